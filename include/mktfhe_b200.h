@@ -1,0 +1,138 @@
+/* mktfhe_b200.h -- C-ABI of the B200 (sm_100a) gate-bootstrapping library libmktfhe_b200.so.
+ *
+ * The reference (SNUCP/MKTFHE, Julia) has no FFI; this header defines the boundary a Julia `ccall`
+ * binding uses (julia/MKTFHEB200.jl).  The cut is the reference's
+ *   bootstrapping!(ctxt, scheme)        /root/reference/src/tfhe/bootstrapping.jl:4-27
+ *   NAND/AND/OR/XOR/XNOR/NOR            /root/reference/src/tfhe/gate.jl:1-52
+ * plus a one-time key upload hooked after `setup` (/root/reference/src/tfhe/scheme.jl:151,190,244,292,343).
+ * Key generation, encryption and decryption stay on the host (the reference's own code, or
+ * mktfhe_host.h when Julia is absent).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Unless a name ends in _dev, pointers are HOST pointers, borrowed
+ *     for the duration of the call; the library copies what it keeps and owns all device memory.
+ *   - Every function returns 0 on success or a negative mktfhe_status; mktfhe_last_error() gives text.
+ *     No exception crosses the boundary and the library never calls back into the host language.
+ *   - One context belongs to one device and is used from one host thread at a time.  Multi-GPU = one
+ *     context per device (one process per GPU under torchrun, or one per device inside one process);
+ *     gates are independent, so the caller shards the batch and no collective is involved.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     MKTFHE_ERR_CUDA.
+ *
+ * Flat layouts (SURVEY App. E traversal order; "complex" = interleaved (re, im) doubles in the
+ * reference's slot order, i.e. exactly the Vector{ComplexF64} of a TransNativePoly; H = N/2):
+ *   brk  RGSW schemes (CGGI, LMSS, KMS, KMS_BLOCK), per party
+ *          [idx < n][basket: 0 = basketb, 1 = basketa[1]][j < l_gsw][comp: 0 = .b, 1 = .a[1]][H] complex
+ *          = scheme.btk[p].brk[idx]   (keygen.jl:12-14,39-41,106-108,143-145; read at bootstrapping.jl:63-68,427-432)
+ *   brk  CCS, per party   [idx < n][j < l_uni][0 = d[j], 1 = f.stack[j].b, 2 = f.stack[j].a[1]][H] complex
+ *          = scheme.btk[p].brk[idx]::TransUniEnc   (keygen.jl:71-73; read at bootstrapping.jl:280-319)
+ *   rlk  KMS*, per party  [j < l_uni][0 = d[j], 1 = f.stack[j].b, 2 = f.stack[j].a[1]][H] complex   (keygen.jl:103,139)
+ *   pubb CCS, KMS*, per party  [j < l_uni][H] complex = btk[p].b   (keygen.jl:68,100,136)
+ *   crs  CCS, KMS*        [j < l_uni][H] complex = scheme.a        (scheme.jl:251,298,349)
+ *   ksk  per party        [c < N][digit-1 < Dk][level < f][1 + n] uint32: .b then .a of
+ *          btk[p].ksk[digit, c+1].stack[level+1]; Dk = D-1 (CGGI, CCS, KMS) or D/2 (LMSS, KMS_BLOCK, where
+ *          rows c < n are never read)   (keygen.jl:16-24,43-52,75-79,110-114,147-151)
+ *   LWE ciphertext   uint32 [1 + n*k]: b, then a in party-major blocks of n   (lwe.jl:1-9, scheme.jl:379-386)
+ *   RLWE accumulator torus [(k+1)][N]: b, a_1..a_k; torus = uint64 for KMS*, uint32 otherwise
+ *   levkeys (KMS* phase-1 output)  [R][2][H] complex per gate, R = 1 + (k-1)*l_lev rows:
+ *          party 0 row 0, then party p >= 1 rows 1 + (p-1)*l_lev + r   (bootstrapping.jl:400-409,441-442)
+ */
+#ifndef MKTFHE_B200_H
+#define MKTFHE_B200_H
+#include "mktfhe_params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mktfhe_ctx mktfhe_ctx;
+
+enum mktfhe_status {
+    MKTFHE_OK = 0,
+    MKTFHE_ERR_PARAMS = -1,      /* unsupported or inconsistent parameters */
+    MKTFHE_ERR_CUDA = -2,        /* CUDA runtime error, or no device */
+    MKTFHE_ERR_STATE = -3,       /* keys missing / not finalized */
+    MKTFHE_ERR_ARG = -4          /* null pointer, bad party index, bad opcode */
+};
+
+/* Arithmetic mode of the floating-point stages.
+ *   STRICT: the reference's butterfly schedule, slot order and operation order with no FMA contraction;
+ *           bit-identical to the CPU oracle on every ciphertext coefficient (tests/test_gpu_strict.py).
+ *   FAST:   the production path: register-resident FFT with fused multiply-add and its own slot order.
+ *           Integer stages stay bit-exact; accumulator coefficients differ from STRICT only by FFT
+ *           rounding (per-step tolerance in tests/test_gpu_fast.py).  Default. */
+enum mktfhe_mode { MKTFHE_MODE_STRICT = 0, MKTFHE_MODE_FAST = 1 };
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* Replaces: scheme construction in `setup` (scheme.jl:151-166,190-205,244-252,292-299,343-350). */
+int mktfhe_ctx_create(const mktfhe_params *params, int device, mktfhe_ctx **out);
+void mktfhe_ctx_destroy(mktfhe_ctx *ctx);
+const char *mktfhe_last_error(const mktfhe_ctx *ctx);   /* ctx may be NULL: last creation error */
+int mktfhe_set_mode(mktfhe_ctx *ctx, int mode);
+int mktfhe_get_mode(const mktfhe_ctx *ctx);
+
+/* ---- one-time key upload --------------------------------------------------------------------- */
+/* Replaces: holding `btk[party]` in the scheme struct (scheme.jl:107-116,209-219,256-265,301-312).
+ * rlk / pubb may be NULL for schemes that have none. party = 0 for CGGI / LMSS. */
+int mktfhe_upload_party_key(mktfhe_ctx *ctx, int party, const double *brk, const double *rlk,
+                            const double *pubb, const uint32_t *ksk);
+/* Replaces: `fft(a, ffter)` stored as scheme.a (scheme.jl:251,298,349). NULL for CGGI / LMSS. */
+int mktfhe_upload_common(mktfhe_ctx *ctx, const double *crs_fft);
+/* Builds the transform tables (fft.jl:26-44) and monomial table (scheme.jl:121-146) on the device and
+ * the FAST-mode key layouts.  Must be called once after all uploads. */
+int mktfhe_finalize_keys(mktfhe_ctx *ctx);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* Replaces: NAND ... NOR (gate.jl:1-52) over a batch: out[g] = bootstrap(linear(in1[g], in2[g])).
+ * batch = 1 is the reference's per-gate call.  Host buffers; H2D and D2H copies are inside the call. */
+int mktfhe_gate_batch(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2,
+                      uint32_t *out, size_t batch);
+/* Replaces: bootstrapping!(ctxt, scheme) (bootstrapping.jl:4-27) over a batch (out may alias in). */
+int mktfhe_bootstrap_batch(mktfhe_ctx *ctx, const uint32_t *in, uint32_t *out, size_t batch);
+/* Same with ciphertexts already resident in device memory of ctx's device (no copies, asynchronous on
+ * the context stream; call mktfhe_sync before reading).  gate_op < 0 means bootstrap of in1 only. */
+int mktfhe_gate_batch_dev(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1_dev, const uint32_t *in2_dev,
+                          uint32_t *out_dev, size_t batch);
+int mktfhe_sync(mktfhe_ctx *ctx);
+/* The CUDA stream (cudaStream_t) all work of this context is launched on, for event timing. */
+void *mktfhe_stream(mktfhe_ctx *ctx);
+
+/* ---- parity / debug hooks (host buffers) ------------------------------------------------------- */
+/* gate.jl linear part only. */
+int mktfhe_gate_linear_batch(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2,
+                             uint32_t *out, size_t batch);
+/* bootstrapping.jl:8-9: tilde[g] = [b~, a~...] (1 + n*k words). */
+int mktfhe_modswitch_batch(mktfhe_ctx *ctx, const uint32_t *lwe, uint32_t *tilde, size_t batch);
+/* Test vector + blind rotation (bootstrapping.jl:11-25): lwe -> accumulator [(k+1)][N] torus per gate. */
+int mktfhe_blindrotate_batch(mktfhe_ctx *ctx, const uint32_t *lwe, void *acc_out, size_t batch);
+/* KMS* phase 1 only (bootstrapping.jl:389-443, 599-659): lwe -> levkeys [R][2][H] complex per gate,
+ * always in the reference's slot order. */
+int mktfhe_phase1_batch(mktfhe_ctx *ctx, const uint32_t *lwe, double *levkeys_out, size_t batch);
+/* Key switch only (bootstrapping.jl:81-109,170-229,333-364,564-594,664-695): accumulator -> LWE. */
+int mktfhe_keyswitch_batch(mktfhe_ctx *ctx, const void *acc, uint32_t *lwe_out, size_t batch);
+/* One loop iteration of phase 1 / CGGI on `batch` independent RLWE rows [2][N] torus, all against
+ * brk[party][idx] with rotation atilde[g]:  acc += ifft(monomial[atilde] * (acc [.] brk))
+ * (bootstrapping.jl:47-74, 413-438). */
+int mktfhe_cmux_step_batch(mktfhe_ctx *ctx, int party, int idx, const uint32_t *atilde, void *acc_rows,
+                           size_t batch);
+/* fftto! / ifftto! (fft.jl:57-63,74-81) and poly decompto! (gsw.jl:86-96) on `batch` polynomials.
+ * bits = 32 / 64 selects the torus; spectra in the reference's slot order; STRICT arithmetic. */
+int mktfhe_fft_batch(mktfhe_ctx *ctx, int bits, const void *polys, double *spectra, size_t batch);
+int mktfhe_ifft_batch(mktfhe_ctx *ctx, int bits, const double *spectra, void *polys, size_t batch);
+int mktfhe_decomp_batch(mktfhe_ctx *ctx, int bits, int l, int logB, const void *polys, void *digits,
+                        size_t batch);
+
+/* ---- measurement ----------------------------------------------------------------------------- */
+/* Device time (ms, CUDA events on the context stream) spent in each stage of the most recent
+ * gate/bootstrap batch call, and the number of kernel launches it made. */
+enum mktfhe_stage { MKTFHE_STAGE_PREP = 0, MKTFHE_STAGE_PHASE1 = 1, MKTFHE_STAGE_PHASE2 = 2,
+                    MKTFHE_STAGE_KEYSWITCH = 3, MKTFHE_STAGE_COUNT = 4 };
+int mktfhe_last_stage_ms(mktfhe_ctx *ctx, float *ms_out /* [MKTFHE_STAGE_COUNT] */, int *launches_out);
+/* Measured FP64 FMA peak of the device (TFLOP/s, 2 flops per DFMA) from a register-only DFMA loop:
+ * the FP64 roofline denominator MEASURED_PEAKS.json lacks. */
+int mktfhe_measure_dfma_peak(mktfhe_ctx *ctx, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

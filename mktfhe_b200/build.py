@@ -74,7 +74,7 @@ def build_cuda(force: bool = False) -> str:
     deps = srcs + [os.path.join(CSRC, d) for d in CUDA_DEPS] + \
         [os.path.join(INCLUDE, h) for h in ("mktfhe_b200.h", "mktfhe_params.h")]
     if force or _stale(CUDA_LIB, deps):
-        _run([nvcc_path()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", CUDA_LIB] + srcs,
+        _run([nvcc_path()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", CUDA_LIB] + srcs + ["-lquadmath"],
              log=os.path.join(LIBDIR, "nvcc_build.log"))
     return CUDA_LIB
 

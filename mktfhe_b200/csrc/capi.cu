@@ -1,0 +1,675 @@
+// capi.cu -- C-ABI of include/mktfhe_b200.h: context, key upload, batch pipeline, parity hooks.
+#include "../../include/mktfhe_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <quadmath.h>
+
+#include "common.cuh"
+#include "fft_strict.cuh"
+#include "kernels_strict.cuh"
+#include "keyswitch.cuh"
+#include "kernels_fast.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+struct StageEvents { cudaEvent_t e[MKTFHE_STAGE_COUNT + 1]; };
+
+}  // namespace
+
+struct mktfhe_ctx {
+    mktfhe_params p;
+    int device = 0, mode = MKTFHE_MODE_STRICT;
+    int N = 0, H = 0, bits = 32, R = 1, nparties = 1;
+    bool mk = false, kms = false, block = false;
+    cudaStream_t stream = nullptr;
+    // tables / keys (device)
+    cplx *psi = nullptr, *psiinv = nullptr, *roots = nullptr, *rootsinv = nullptr, *mono = nullptr;
+    std::vector<cplx *> brk, rlk, pubb;
+    std::vector<uint32_t *> ksk;
+    cplx *crs = nullptr;
+    cplx **d_brk = nullptr, **d_rlk = nullptr, **d_pubb = nullptr;
+    uint32_t **d_ksk = nullptr;
+    bool finalized = false;
+    FastKeys fast;
+    // workspace for `cap` gates
+    size_t cap = 0;
+    uint32_t *w_in1 = nullptr, *w_in2 = nullptr, *w_out = nullptr, *w_lin = nullptr, *w_tilde = nullptr, *w_v = nullptr;
+    void *w_acc = nullptr;
+    cplx *w_lev = nullptr, *w_tx = nullptr, *w_ty = nullptr;
+    // measurement
+    std::vector<StageEvents> events;
+    size_t events_used = 0;
+    int launches = 0;
+    std::string err;
+    size_t mem_budget = (size_t)24 << 30;
+
+    FftTables tables() const { return FftTables{psi, psiinv, roots, rootsinv}; }
+};
+
+namespace {
+
+int fail(mktfhe_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, MKTFHE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
+
+size_t per_gate_bytes(const mktfhe_ctx *c) {
+    const mktfhe_params &p = c->p;
+    size_t b = 5 * mktfhe_lwe_words(&p) * 4;                                   // in1, in2, out, lin, tilde
+    b += (size_t)(p.k + 1) * c->N * (c->bits / 8);                             // acc
+    if (c->kms) b += (size_t)c->R * 2 * c->H * 16 + 2 * (size_t)(p.k + 1) * c->H * 16;
+    if (p.scheme == MKTFHE_CCS) b += (size_t)(p.k + 1) * c->N * 4 + (size_t)(p.k + 1) * c->H * 16;
+    return b;
+}
+
+void free_workspace(mktfhe_ctx *c) {
+    dfree(c->w_in1); dfree(c->w_in2); dfree(c->w_out); dfree(c->w_lin); dfree(c->w_tilde); dfree(c->w_v);
+    dfree(c->w_acc); dfree(c->w_lev); dfree(c->w_tx); dfree(c->w_ty);
+    c->cap = 0;
+}
+
+int ensure_workspace(mktfhe_ctx *ctx, size_t gates) {
+    if (gates <= ctx->cap) return 0;
+    free_workspace(ctx);
+    const mktfhe_params &p = ctx->p;
+    const size_t lw = mktfhe_lwe_words(&p);
+    CK(cudaMalloc(&ctx->w_in1, gates * lw * 4));
+    CK(cudaMalloc(&ctx->w_in2, gates * lw * 4));
+    CK(cudaMalloc(&ctx->w_out, gates * lw * 4));
+    CK(cudaMalloc(&ctx->w_lin, gates * lw * 4));
+    CK(cudaMalloc(&ctx->w_tilde, gates * lw * 4));
+    CK(cudaMalloc(&ctx->w_acc, gates * (size_t)(p.k + 1) * ctx->N * (ctx->bits / 8)));
+    if (ctx->kms) {
+        CK(cudaMalloc(&ctx->w_lev, gates * (size_t)ctx->R * 2 * ctx->H * sizeof(cplx)));
+        CK(cudaMalloc(&ctx->w_tx, gates * (size_t)(p.k + 1) * ctx->H * sizeof(cplx)));
+        CK(cudaMalloc(&ctx->w_ty, gates * (size_t)(p.k + 1) * ctx->H * sizeof(cplx)));
+    }
+    if (p.scheme == MKTFHE_CCS) {
+        CK(cudaMalloc(&ctx->w_v, gates * (size_t)(p.k + 1) * ctx->N * 4));
+        CK(cudaMalloc(&ctx->w_tx, gates * (size_t)(p.k + 1) * ctx->H * sizeof(cplx)));
+    }
+    ctx->cap = gates;
+    return 0;
+}
+
+size_t chunk_gates(const mktfhe_ctx *c, size_t batch) {
+    const size_t lim = c->mem_budget / per_gate_bytes(c);
+    return batch < lim ? batch : (lim ? lim : 1);
+}
+
+// ---- kernel launchers (one per stage) ---------------------------------------------------------------
+template <class T, int H, int ELL>
+int launch_rgsw(mktfhe_ctx *ctx, const RgswArgs &a, size_t units) {
+    auto kern = k_rgsw_blindrotate<T, H, ELL>;
+    const size_t smem = rgsw_smem_bytes<T, H>();
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)units, MK_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_rgsw(mktfhe_ctx *ctx, RgswArgs a, size_t units) {
+    const mktfhe_params &p = ctx->p;
+    a.brk = ctx->d_brk; a.mono = ctx->mono; a.tb = ctx->tables();
+    a.n = p.n; a.d = p.d; a.k = p.k; a.l = p.l_gsw; a.logB = p.logB_gsw;
+    a.l_lev = p.l_lev; a.logB_lev = p.logB_lev; a.R = ctx->R; a.lwe_words = (int)mktfhe_lwe_words(&p);
+    const bool blk = ctx->block && a.mode != RG_MODE_STEP;
+    if (ctx->bits == 64) return blk ? launch_rgsw<uint64_t, 1024, 3>(ctx, a, units) : launch_rgsw<uint64_t, 1024, 1>(ctx, a, units);
+    return blk ? launch_rgsw<uint32_t, 512, 3>(ctx, a, units) : launch_rgsw<uint32_t, 512, 1>(ctx, a, units);
+}
+
+int run_prep(mktfhe_ctx *ctx, int op, const uint32_t *in1, const uint32_t *in2, uint32_t *lin, uint32_t *tilde, size_t gates) {
+    const size_t total = gates * mktfhe_lwe_words(&ctx->p);
+    int logN = 0; while ((1 << logN) < ctx->N) logN++;
+    k_gate_prep<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in1, in2, lin, tilde, op, (int)mktfhe_lwe_words(&ctx->p), total, 32 - logN - 1);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_phase1(mktfhe_ctx *ctx, const uint32_t *tilde, cplx *lev, size_t gates) {
+    if (ctx->mode == MKTFHE_MODE_FAST) return fast_phase1(ctx->fast, ctx->p, tilde, lev, gates, ctx->stream, &ctx->launches, ctx->err);
+    RgswArgs a{};
+    a.tilde = tilde; a.lev_out = lev; a.mode = RG_MODE_KMS;
+    return run_rgsw(ctx, a, gates * ctx->R);
+}
+
+int run_phase2(mktfhe_ctx *ctx, const uint32_t *tilde, const cplx *lev, uint64_t *acc, size_t gates) {
+    const mktfhe_params &p = ctx->p;
+    Phase2Args a{};
+    a.tilde = tilde; a.lev = lev; a.rlk = ctx->d_rlk; a.pubb = ctx->d_pubb; a.crs = ctx->crs; a.tb = ctx->tables();
+    a.acc = acc; a.tx = ctx->w_tx; a.ty = ctx->w_ty;
+    a.k = p.k; a.l_lev = p.l_lev; a.logB_lev = p.logB_lev; a.l_uni = p.l_uni; a.logB_uni = p.logB_uni;
+    a.R = ctx->R; a.lwe_words = (int)mktfhe_lwe_words(&p);
+    auto kern = k_kms_phase2<1024>;
+    const size_t smem = phase2_smem_bytes<1024>();
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)gates, MK_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_ccs(mktfhe_ctx *ctx, const uint32_t *tilde, uint32_t *acc, size_t gates) {
+    const mktfhe_params &p = ctx->p;
+    CcsArgs a{};
+    a.tilde = tilde; a.brk = ctx->d_brk; a.pubb = ctx->d_pubb; a.crs = ctx->crs; a.mono = ctx->mono; a.tb = ctx->tables();
+    a.acc = acc; a.vscr = ctx->w_v; a.tacc = ctx->w_tx;
+    a.n = p.n; a.k = p.k; a.l_uni = p.l_uni; a.logB_uni = p.logB_uni; a.lwe_words = (int)mktfhe_lwe_words(&p);
+    auto kern = k_ccs_blindrotate<512>;
+    const size_t smem = ccs_smem_bytes<512>();
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)gates, MK_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_keyswitch(mktfhe_ctx *ctx, const void *acc, uint32_t *out, size_t gates) {
+    const mktfhe_params &p = ctx->p;
+    KsArgs a{};
+    a.acc = acc; a.ksk = ctx->d_ksk; a.out = out;
+    a.N = ctx->N; a.n = p.n; a.k = p.k; a.f = p.f; a.logD = p.logD; a.Dk = mktfhe_ksk_rows(&p);
+    a.bits64 = ctx->bits == 64; a.block = ctx->block;
+    const size_t smem = keyswitch_smem_bytes(ctx->N, p.f, p.n);
+    k_keyswitch<<<(unsigned)gates, MK_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// blind rotation of `gates` ciphertexts whose tilde is in w_tilde -> w_acc
+int run_blindrotate(mktfhe_ctx *ctx, const uint32_t *tilde, size_t gates, StageEvents *ev) {
+    const mktfhe_params &p = ctx->p;
+    int rc;
+    if (ctx->kms) {
+        if ((rc = run_phase1(ctx, tilde, ctx->w_lev, gates))) return rc;
+        if (ev) cudaEventRecord(ev->e[2], ctx->stream);
+        if ((rc = run_phase2(ctx, tilde, ctx->w_lev, (uint64_t *)ctx->w_acc, gates))) return rc;
+    } else if (p.scheme == MKTFHE_CCS) {
+        if ((rc = run_ccs(ctx, tilde, (uint32_t *)ctx->w_acc, gates))) return rc;
+        if (ev) cudaEventRecord(ev->e[2], ctx->stream);
+    } else {
+        RgswArgs a{};
+        a.tilde = tilde; a.acc_io = ctx->w_acc; a.mode = RG_MODE_SK;
+        if ((rc = run_rgsw(ctx, a, gates))) return rc;
+        if (ev) cudaEventRecord(ev->e[2], ctx->stream);
+    }
+    return 0;
+}
+
+int check_ready(mktfhe_ctx *ctx) {
+    if (!ctx) return MKTFHE_ERR_ARG;
+    if (!ctx->finalized) return fail(ctx, MKTFHE_ERR_STATE, "keys not finalized: call mktfhe_finalize_keys first");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(ctx, MKTFHE_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+StageEvents *next_events(mktfhe_ctx *ctx) {
+    if (ctx->events_used == ctx->events.size()) {
+        StageEvents s;
+        for (auto &e : s.e) if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ctx->events.push_back(s);
+    }
+    return &ctx->events[ctx->events_used++];
+}
+
+void fft_tables_host(int N, std::vector<cplx> &psi, std::vector<cplx> &psiinv, std::vector<cplx> &roots, std::vector<cplx> &rootsinv) {
+    // fft.jl:26-44.  BigFloat in the reference, binary128 here; both round to the same Float64.
+    const int H = N / 2;
+    psi.resize(H); psiinv.resize(H); roots.resize(H); rootsinv.resize(H);
+    for (int j = 0; j < H; j++) {
+        const __float128 pi = acosq((__float128)-1), th = pi * j / H, ph = pi * j / N;
+        psi[j] = make_double2((double)cosq(th), (double)-sinq(th));
+        psiinv[j] = make_double2((double)cosq(th), (double)sinq(th));
+        roots[j] = make_double2((double)cosq(ph), (double)sinq(ph));
+        rootsinv[j] = make_double2((double)(cosq(ph) / H), (double)(-sinq(ph) / H));
+    }
+    auto bitrev = [&](std::vector<cplx> &v) {
+        for (int i = 1, j = 0; i < H; i++) {
+            int bit = H >> 1;
+            for (; j >= bit; bit >>= 1) j -= bit;
+            j += bit;
+            if (i < j) std::swap(v[i], v[j]);
+        }
+    };
+    bitrev(psi); bitrev(psiinv);
+}
+
+template <class T> int upload(mktfhe_ctx *ctx, T *&dst, const void *src, size_t bytes) {
+    dfree(dst);
+    CK(cudaMalloc(&dst, bytes));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+__global__ void k_dfma_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+template <class T> int fft_hook(mktfhe_ctx *ctx, bool inverse, const void *in, void *out, size_t batch) {
+    const int H = ctx->H, N = ctx->N;
+    T *d_poly = nullptr; cplx *d_spec = nullptr;
+    CK(cudaMalloc(&d_poly, batch * N * sizeof(T)));
+    CK(cudaMalloc(&d_spec, batch * H * sizeof(cplx)));
+    const int G = MK_THREADS / (H / 8);
+    const size_t smem = (size_t)G * padded_len(H) * sizeof(cplx);
+    const unsigned grid = (unsigned)((batch + G - 1) / G);
+    if (!inverse) {
+        CK(cudaMemcpyAsync(d_poly, in, batch * N * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        if (H == 1024) k_fft_batch<T, 1024><<<grid, MK_THREADS, smem, ctx->stream>>>(d_poly, d_spec, ctx->tables(), (int)batch);
+        else k_fft_batch<T, 512><<<grid, MK_THREADS, smem, ctx->stream>>>(d_poly, d_spec, ctx->tables(), (int)batch);
+        CK(cudaMemcpyAsync(out, d_spec, batch * H * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        CK(cudaMemcpyAsync(d_spec, in, batch * H * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+        if (H == 1024) k_ifft_batch<T, 1024><<<grid, MK_THREADS, smem, ctx->stream>>>(d_spec, d_poly, ctx->tables(), (int)batch);
+        else k_ifft_batch<T, 512><<<grid, MK_THREADS, smem, ctx->stream>>>(d_spec, d_poly, ctx->tables(), (int)batch);
+        CK(cudaMemcpyAsync(out, d_poly, batch * N * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_poly); cudaFree(d_spec);
+    return 0;
+}
+
+template <class T> int decomp_hook(mktfhe_ctx *ctx, int l, int logB, const void *polys, void *digits, size_t batch) {
+    const int N = ctx->N;
+    const size_t total = batch * N;
+    T *d_in = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_in, total * sizeof(T)));
+    CK(cudaMalloc(&d_out, total * l * sizeof(T)));
+    CK(cudaMemcpyAsync(d_in, polys, total * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    k_decomp_batch<T><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_in, d_out, N, l, logB, total);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(digits, d_out, total * l * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_in); cudaFree(d_out);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mktfhe_last_error(const mktfhe_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mktfhe_ctx_create(const mktfhe_params *params, int device, mktfhe_ctx **out) {
+    mktfhe_ctx *ctx = nullptr;   // for CK/fail before allocation
+    if (!params || !out) return fail(nullptr, MKTFHE_ERR_ARG, "null argument");
+    *out = nullptr;
+    const mktfhe_params &p = *params;
+    const bool kms = p.scheme == MKTFHE_KMS || p.scheme == MKTFHE_KMS_BLOCK;
+    const bool blk = p.scheme == MKTFHE_LMSS || p.scheme == MKTFHE_KMS_BLOCK;
+    const bool mk = kms || p.scheme == MKTFHE_CCS;
+    if (p.scheme < 0 || p.scheme > MKTFHE_KMS_BLOCK) return fail(nullptr, MKTFHE_ERR_PARAMS, "unknown scheme");
+    if (kms ? p.N != 2048 : p.N != 1024)
+        return fail(nullptr, MKTFHE_ERR_PARAMS, "ring dimension: KMS* needs N = 2048, CGGI/LMSS/CCS need N = 1024 (params.jl)");
+    if (!mk && p.k != 1) return fail(nullptr, MKTFHE_ERR_PARAMS, "single-key schemes support RLWE length k = 1 only");
+    if (blk && (p.ell != 3 || p.d * p.ell != p.n)) return fail(nullptr, MKTFHE_ERR_PARAMS, "block schemes need ell = 3 and n = d*ell");
+    if (p.n + 1 > 3 * MK_THREADS || p.n < 1 || p.k < 1) return fail(nullptr, MKTFHE_ERR_PARAMS, "n out of range (1..767)");
+    if (p.f * p.logD > 32 || p.f > 16 || p.logD < 1 || p.logD > 7) return fail(nullptr, MKTFHE_ERR_PARAMS, "key-switch gadget out of range");
+    const int lmax = p.l_gsw > p.l_uni ? (p.l_gsw > p.l_lev ? p.l_gsw : p.l_lev) : (p.l_uni > p.l_lev ? p.l_uni : p.l_lev);
+    if (lmax > MK_MAXL) return fail(nullptr, MKTFHE_ERR_PARAMS, "gadget length above 16");
+    const int w = kms ? 64 : 32;
+    if (p.l_gsw * p.logB_gsw > w || p.l_lev * p.logB_lev > w || p.l_uni * p.logB_uni > w)
+        return fail(nullptr, MKTFHE_ERR_PARAMS, "gadget l*logB exceeds the torus width");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MKTFHE_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, MKTFHE_ERR_ARG, "bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, MKTFHE_ERR_CUDA, cudaGetErrorString(e));
+
+    ctx = new mktfhe_ctx;
+    ctx->p = p; ctx->device = device;
+    ctx->N = p.N; ctx->H = p.N / 2; ctx->bits = w;
+    ctx->kms = kms; ctx->block = blk; ctx->mk = mk;
+    ctx->nparties = mk ? p.k : 1;
+    ctx->R = kms ? 1 + (p.k - 1) * p.l_lev : 1;
+    ctx->brk.assign(ctx->nparties, nullptr); ctx->rlk.assign(ctx->nparties, nullptr);
+    ctx->pubb.assign(ctx->nparties, nullptr); ctx->ksk.assign(ctx->nparties, nullptr);
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return fail(nullptr, MKTFHE_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = ctx;
+    return 0;
+}
+
+void mktfhe_ctx_destroy(mktfhe_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_workspace(ctx);
+    fast_free(ctx->fast);
+    for (auto &q : ctx->brk) dfree(q);
+    for (auto &q : ctx->rlk) dfree(q);
+    for (auto &q : ctx->pubb) dfree(q);
+    for (auto &q : ctx->ksk) dfree(q);
+    dfree(ctx->crs); dfree(ctx->psi); dfree(ctx->psiinv); dfree(ctx->roots); dfree(ctx->rootsinv); dfree(ctx->mono);
+    dfree(ctx->d_brk); dfree(ctx->d_rlk); dfree(ctx->d_pubb); dfree(ctx->d_ksk);
+    for (auto &s : ctx->events) for (auto &ev : s.e) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int mktfhe_set_mode(mktfhe_ctx *ctx, int mode) {
+    if (!ctx) return MKTFHE_ERR_ARG;
+    if (mode != MKTFHE_MODE_STRICT && mode != MKTFHE_MODE_FAST) return fail(ctx, MKTFHE_ERR_ARG, "bad mode");
+    if (mode == MKTFHE_MODE_FAST && !fast_supported(ctx->p)) return fail(ctx, MKTFHE_ERR_PARAMS, "FAST mode covers KMS / KMS_BLOCK phase 1; this scheme runs STRICT");
+    ctx->mode = mode;
+    return 0;
+}
+int mktfhe_get_mode(const mktfhe_ctx *ctx) { return ctx ? ctx->mode : MKTFHE_ERR_ARG; }
+
+int mktfhe_upload_party_key(mktfhe_ctx *ctx, int party, const double *brk, const double *rlk, const double *pubb, const uint32_t *ksk) {
+    if (!ctx) return MKTFHE_ERR_ARG;
+    if (party < 0 || party >= ctx->nparties) return fail(ctx, MKTFHE_ERR_ARG, "bad party index");
+    if (!brk || !ksk) return fail(ctx, MKTFHE_ERR_ARG, "brk and ksk are required");
+    if (ctx->kms && (!rlk || !pubb)) return fail(ctx, MKTFHE_ERR_ARG, "KMS needs rlk and pubb");
+    if (ctx->p.scheme == MKTFHE_CCS && !pubb) return fail(ctx, MKTFHE_ERR_ARG, "CCS needs pubb");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = upload(ctx, ctx->brk[party], brk, mktfhe_brk_doubles(&ctx->p) * 8))) return rc;
+    if ((rc = upload(ctx, ctx->ksk[party], ksk, mktfhe_ksk_words(&ctx->p) * 4))) return rc;
+    if (ctx->kms && (rc = upload(ctx, ctx->rlk[party], rlk, mktfhe_rlk_doubles(&ctx->p) * 8))) return rc;
+    if (ctx->mk && (rc = upload(ctx, ctx->pubb[party], pubb, mktfhe_pubb_doubles(&ctx->p) * 8))) return rc;
+    ctx->finalized = false;
+    return 0;
+}
+
+int mktfhe_upload_common(mktfhe_ctx *ctx, const double *crs_fft) {
+    if (!ctx) return MKTFHE_ERR_ARG;
+    if (!ctx->mk) return 0;
+    if (!crs_fft) return fail(ctx, MKTFHE_ERR_ARG, "crs_fft is required for CCS / KMS");
+    CK(cudaSetDevice(ctx->device));
+    ctx->finalized = false;
+    return upload(ctx, ctx->crs, crs_fft, mktfhe_crs_doubles(&ctx->p) * 8);
+}
+
+int mktfhe_finalize_keys(mktfhe_ctx *ctx) {
+    if (!ctx) return MKTFHE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < ctx->nparties; i++)
+        if (!ctx->brk[i] || !ctx->ksk[i]) return fail(ctx, MKTFHE_ERR_STATE, "party key missing: " + std::to_string(i));
+    if (ctx->mk && !ctx->crs) return fail(ctx, MKTFHE_ERR_STATE, "common reference string missing");
+    int rc;
+    std::vector<cplx> psi, psiinv, roots, rootsinv;
+    fft_tables_host(ctx->N, psi, psiinv, roots, rootsinv);
+    const size_t tb = sizeof(cplx) * ctx->H;
+    if ((rc = upload(ctx, ctx->psi, psi.data(), tb)) || (rc = upload(ctx, ctx->psiinv, psiinv.data(), tb)) ||
+        (rc = upload(ctx, ctx->roots, roots.data(), tb)) || (rc = upload(ctx, ctx->rootsinv, rootsinv.data(), tb)))
+        return rc;
+    if ((rc = upload(ctx, ctx->d_brk, ctx->brk.data(), sizeof(void *) * ctx->nparties))) return rc;
+    if ((rc = upload(ctx, ctx->d_ksk, ctx->ksk.data(), sizeof(void *) * ctx->nparties))) return rc;
+    if ((rc = upload(ctx, ctx->d_rlk, ctx->rlk.data(), sizeof(void *) * ctx->nparties))) return rc;
+    if ((rc = upload(ctx, ctx->d_pubb, ctx->pubb.data(), sizeof(void *) * ctx->nparties))) return rc;
+    // monomial table, built with the same transform the reference uses (scheme.jl:121-146)
+    dfree(ctx->mono);
+    CK(cudaMalloc(&ctx->mono, sizeof(cplx) * (size_t)2 * ctx->N * ctx->H));
+    if (ctx->H == 1024) {
+        const int G = MK_THREADS / (1024 / 8);
+        const size_t smem = (size_t)G * padded_len(1024) * sizeof(cplx);
+        k_build_monomials<1024><<<(2 * ctx->N + G - 1) / G, MK_THREADS, smem, ctx->stream>>>(ctx->mono, ctx->tables());
+    } else {
+        const int G = MK_THREADS / (512 / 8);
+        const size_t smem = (size_t)G * padded_len(512) * sizeof(cplx);
+        k_build_monomials<512><<<(2 * ctx->N + G - 1) / G, MK_THREADS, smem, ctx->stream>>>(ctx->mono, ctx->tables());
+    }
+    CK(cudaGetLastError());
+    if (fast_supported(ctx->p)) {
+        if ((rc = fast_build(ctx->fast, ctx->p, ctx->brk, ctx->stream, ctx->err))) return rc;
+        ctx->mode = MKTFHE_MODE_FAST;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->finalized = true;
+    return 0;
+}
+
+int mktfhe_sync(mktfhe_ctx *ctx) {
+    if (!ctx) return MKTFHE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+void *mktfhe_stream(mktfhe_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+static int run_pipeline(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2, uint32_t *out, size_t g) {
+    int rc;
+    StageEvents *ev = next_events(ctx);
+    if (!ev) return fail(ctx, MKTFHE_ERR_CUDA, "cudaEventCreate failed");
+    cudaEventRecord(ev->e[0], ctx->stream);
+    if ((rc = run_prep(ctx, gate_op, in1, in2, nullptr, ctx->w_tilde, g))) return rc;
+    cudaEventRecord(ev->e[1], ctx->stream);
+    if ((rc = run_blindrotate(ctx, ctx->w_tilde, g, ev))) return rc;
+    cudaEventRecord(ev->e[3], ctx->stream);
+    if ((rc = run_keyswitch(ctx, ctx->w_acc, out, g))) return rc;
+    cudaEventRecord(ev->e[4], ctx->stream);
+    return 0;
+}
+
+int mktfhe_gate_batch_dev(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2, uint32_t *out, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (!in1 || !out || (gate_op >= 0 && !in2)) return fail(ctx, MKTFHE_ERR_ARG, "null ciphertext pointer");
+    if (gate_op > MKTFHE_NOR) return fail(ctx, MKTFHE_ERR_ARG, "bad gate opcode");
+    if (batch == 0) return 0;
+    const size_t lw = mktfhe_lwe_words(&ctx->p);
+    const size_t chunk = chunk_gates(ctx, batch);
+    if ((rc = ensure_workspace(ctx, chunk))) return rc;
+    ctx->events_used = 0; ctx->launches = 0;
+    for (size_t g0 = 0; g0 < batch; g0 += chunk) {
+        const size_t g = batch - g0 < chunk ? batch - g0 : chunk;
+        if ((rc = run_pipeline(ctx, gate_op, in1 + g0 * lw, in2 ? in2 + g0 * lw : nullptr, out + g0 * lw, g))) return rc;
+    }
+    return 0;
+}
+
+int mktfhe_gate_batch(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2, uint32_t *out, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (!in1 || !out || (gate_op >= 0 && !in2)) return fail(ctx, MKTFHE_ERR_ARG, "null ciphertext pointer");
+    if (gate_op > MKTFHE_NOR) return fail(ctx, MKTFHE_ERR_ARG, "bad gate opcode");
+    if (batch == 0) return 0;
+    const size_t lw = mktfhe_lwe_words(&ctx->p);
+    const size_t chunk = chunk_gates(ctx, batch);
+    if ((rc = ensure_workspace(ctx, chunk))) return rc;
+    ctx->events_used = 0; ctx->launches = 0;
+    // ciphertexts are small (<= 72 KB each); stage one chunk at a time through the workspace
+    for (size_t g0 = 0; g0 < batch; g0 += chunk) {
+        const size_t g = batch - g0 < chunk ? batch - g0 : chunk;
+        CK(cudaMemcpyAsync(ctx->w_in1, in1 + g0 * lw, g * lw * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (gate_op >= 0) CK(cudaMemcpyAsync(ctx->w_in2, in2 + g0 * lw, g * lw * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = run_pipeline(ctx, gate_op, ctx->w_in1, gate_op >= 0 ? ctx->w_in2 : nullptr, ctx->w_out, g))) return rc;
+        CK(cudaMemcpyAsync(out + g0 * lw, ctx->w_out, g * lw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int mktfhe_bootstrap_batch(mktfhe_ctx *ctx, const uint32_t *in, uint32_t *out, size_t batch) {
+    return mktfhe_gate_batch(ctx, -1, in, nullptr, out, batch);
+}
+
+int mktfhe_last_stage_ms(mktfhe_ctx *ctx, float *ms_out, int *launches_out) {
+    if (!ctx || !ms_out) return MKTFHE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < MKTFHE_STAGE_COUNT; s++) ms_out[s] = 0.f;
+    for (size_t i = 0; i < ctx->events_used; i++)
+        for (int s = 0; s < MKTFHE_STAGE_COUNT; s++) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ctx->events[i].e[s], ctx->events[i].e[s + 1]));
+            ms_out[s] += ms;
+        }
+    if (launches_out) *launches_out = ctx->launches;
+    return 0;
+}
+
+// ---- parity / debug hooks -------------------------------------------------------------------------
+
+int mktfhe_gate_linear_batch(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2, uint32_t *out, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (!in1 || !in2 || !out || gate_op < 0 || gate_op > MKTFHE_NOR) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
+    const size_t lw = mktfhe_lwe_words(&ctx->p);
+    if ((rc = ensure_workspace(ctx, batch))) return rc;
+    CK(cudaMemcpyAsync(ctx->w_in1, in1, batch * lw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w_in2, in2, batch * lw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = run_prep(ctx, gate_op, ctx->w_in1, ctx->w_in2, ctx->w_lin, nullptr, batch))) return rc;
+    CK(cudaMemcpyAsync(out, ctx->w_lin, batch * lw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mktfhe_modswitch_batch(mktfhe_ctx *ctx, const uint32_t *lwe, uint32_t *tilde, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (!lwe || !tilde) return fail(ctx, MKTFHE_ERR_ARG, "null pointer");
+    const size_t lw = mktfhe_lwe_words(&ctx->p);
+    if ((rc = ensure_workspace(ctx, batch))) return rc;
+    CK(cudaMemcpyAsync(ctx->w_in1, lwe, batch * lw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = run_prep(ctx, -1, ctx->w_in1, nullptr, nullptr, ctx->w_tilde, batch))) return rc;
+    CK(cudaMemcpyAsync(tilde, ctx->w_tilde, batch * lw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mktfhe_blindrotate_batch(mktfhe_ctx *ctx, const uint32_t *lwe, void *acc_out, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (!lwe || !acc_out) return fail(ctx, MKTFHE_ERR_ARG, "null pointer");
+    const size_t lw = mktfhe_lwe_words(&ctx->p);
+    if ((rc = ensure_workspace(ctx, batch))) return rc;
+    CK(cudaMemcpyAsync(ctx->w_in1, lwe, batch * lw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = run_prep(ctx, -1, ctx->w_in1, nullptr, nullptr, ctx->w_tilde, batch))) return rc;
+    if ((rc = run_blindrotate(ctx, ctx->w_tilde, batch, nullptr))) return rc;
+    CK(cudaMemcpyAsync(acc_out, ctx->w_acc, batch * (size_t)(ctx->p.k + 1) * ctx->N * (ctx->bits / 8), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mktfhe_phase1_batch(mktfhe_ctx *ctx, const uint32_t *lwe, double *levkeys_out, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (!ctx->kms) return fail(ctx, MKTFHE_ERR_PARAMS, "phase 1 exists for KMS / KMS_BLOCK only");
+    if (!lwe || !levkeys_out) return fail(ctx, MKTFHE_ERR_ARG, "null pointer");
+    const size_t lw = mktfhe_lwe_words(&ctx->p);
+    if ((rc = ensure_workspace(ctx, batch))) return rc;
+    CK(cudaMemcpyAsync(ctx->w_in1, lwe, batch * lw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = run_prep(ctx, -1, ctx->w_in1, nullptr, nullptr, ctx->w_tilde, batch))) return rc;
+    if ((rc = run_phase1(ctx, ctx->w_tilde, ctx->w_lev, batch))) return rc;
+    CK(cudaMemcpyAsync(levkeys_out, ctx->w_lev, batch * (size_t)ctx->R * 2 * ctx->H * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mktfhe_keyswitch_batch(mktfhe_ctx *ctx, const void *acc, uint32_t *lwe_out, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (!acc || !lwe_out) return fail(ctx, MKTFHE_ERR_ARG, "null pointer");
+    const size_t lw = mktfhe_lwe_words(&ctx->p);
+    if ((rc = ensure_workspace(ctx, batch))) return rc;
+    CK(cudaMemcpyAsync(ctx->w_acc, acc, batch * (size_t)(ctx->p.k + 1) * ctx->N * (ctx->bits / 8), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = run_keyswitch(ctx, ctx->w_acc, ctx->w_out, batch))) return rc;
+    CK(cudaMemcpyAsync(lwe_out, ctx->w_out, batch * lw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mktfhe_cmux_step_batch(mktfhe_ctx *ctx, int party, int idx, const uint32_t *atilde, void *acc_rows, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (ctx->p.scheme == MKTFHE_CCS) return fail(ctx, MKTFHE_ERR_PARAMS, "CCS has no RGSW step");
+    if (party < 0 || party >= ctx->nparties || idx < 0 || idx >= ctx->p.n || !atilde || !acc_rows) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
+    const size_t row_bytes = (size_t)2 * ctx->N * (ctx->bits / 8);
+    uint32_t *d_at = nullptr; void *d_rows = nullptr;
+    CK(cudaMalloc(&d_at, batch * 4));
+    CK(cudaMalloc(&d_rows, batch * row_bytes));
+    CK(cudaMemcpyAsync(d_at, atilde, batch * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_rows, acc_rows, batch * row_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->mode == MKTFHE_MODE_FAST && fast_supported(ctx->p)) {
+        rc = fast_cmux_step(ctx->fast, ctx->p, party, idx, d_at, d_rows, batch, ctx->stream, &ctx->launches, ctx->err);
+    } else {
+        RgswArgs a{};
+        a.tilde = d_at; a.acc_io = d_rows; a.mode = RG_MODE_STEP; a.step_party = party; a.step_idx = idx;
+        rc = run_rgsw(ctx, a, batch);
+    }
+    if (!rc) {
+        cudaMemcpyAsync(acc_rows, d_rows, batch * row_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, MKTFHE_ERR_CUDA, "cmux step failed");
+    }
+    cudaFree(d_at); cudaFree(d_rows);
+    return rc;
+}
+
+int mktfhe_fft_batch(mktfhe_ctx *ctx, int bits, const void *polys, double *spectra, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (!polys || !spectra || (bits != 32 && bits != 64)) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
+    return bits == 64 ? fft_hook<uint64_t>(ctx, false, polys, spectra, batch) : fft_hook<uint32_t>(ctx, false, polys, spectra, batch);
+}
+
+int mktfhe_ifft_batch(mktfhe_ctx *ctx, int bits, const double *spectra, void *polys, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (!polys || !spectra || (bits != 32 && bits != 64)) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
+    return bits == 64 ? fft_hook<uint64_t>(ctx, true, spectra, polys, batch) : fft_hook<uint32_t>(ctx, true, spectra, polys, batch);
+}
+
+int mktfhe_decomp_batch(mktfhe_ctx *ctx, int bits, int l, int logB, const void *polys, void *digits, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (!polys || !digits || (bits != 32 && bits != 64) || l < 1 || l > MK_MAXL * 2 || logB < 1 || l * logB > bits)
+        return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
+    return bits == 64 ? decomp_hook<uint64_t>(ctx, l, logB, polys, digits, batch) : decomp_hook<uint32_t>(ctx, l, logB, polys, digits, batch);
+}
+
+int mktfhe_measure_dfma_peak(mktfhe_ctx *ctx, double *tflops_out) {
+    if (!ctx || !tflops_out) return MKTFHE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    const int blocks = sms * 8, threads = 256, iters = 1 << 16;
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    k_dfma_peak<<<blocks, threads, 0, ctx->stream>>>(d, iters);     // warm-up
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        k_dfma_peak<<<blocks, threads, 0, ctx->stream>>>(d, iters);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    *tflops_out = (double)blocks * threads * iters * 8 * 2 / (best * 1e-3) / 1e12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return 0;
+}
+
+}  // extern "C"

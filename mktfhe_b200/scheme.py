@@ -1,0 +1,209 @@
+"""Scheme objects: the Python mirror of the reference's `CGGI / LMSS / CCS / KMS / KMS_block` structs
+(/root/reference/src/tfhe/scheme.jl:107-116,168-179,209-219,256-265,301-312) whose `btk` now lives in HBM
+behind an opaque C-ABI context.  `setup(...)` mirrors scheme.jl:151,190,244,292,343.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .keys import KeySet
+from .params import Params
+
+MODE_STRICT, MODE_FAST = 0, 1
+NAND_OP, AND_OP, OR_OP, XOR_OP, XNOR_OP, NOR_OP = range(6)
+STAGES = ("prep", "phase1", "phase2", "keyswitch")
+
+
+class MktfheError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class Scheme:
+    """One device context holding the uploaded evaluation keys of every party."""
+
+    def __init__(self, params: Params, device: int = 0):
+        self.params = params
+        self.device = device
+        self._h = ctypes.c_void_p()
+        L = _lib.lib()
+        cp = params.c_struct()
+        rc = L.mktfhe_ctx_create(ctypes.byref(cp), device, ctypes.byref(self._h))
+        if rc != 0:
+            raise MktfheError(f"mktfhe_ctx_create: {rc}: {L.mktfhe_last_error(None).decode()}")
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.lib().mktfhe_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise MktfheError(f"{what}: {rc}: {_lib.lib().mktfhe_last_error(self._h).decode()}")
+
+    # -- key upload -------------------------------------------------------------------------------
+    def upload_party(self, party: int, brk, ksk, rlk=None, pubb=None):
+        for a in (brk, ksk, rlk, pubb):
+            assert a is None or a.flags["C_CONTIGUOUS"]
+        self._ck(_lib.lib().mktfhe_upload_party_key(self._h, party, _ptr(brk), _ptr(rlk), _ptr(pubb), _ptr(ksk)),
+                 "mktfhe_upload_party_key")
+
+    def upload_common(self, crs_fft):
+        self._ck(_lib.lib().mktfhe_upload_common(self._h, _ptr(crs_fft)), "mktfhe_upload_common")
+
+    def finalize(self):
+        self._ck(_lib.lib().mktfhe_finalize_keys(self._h), "mktfhe_finalize_keys")
+
+    def set_mode(self, mode: int):
+        self._ck(_lib.lib().mktfhe_set_mode(self._h, mode), "mktfhe_set_mode")
+
+    @property
+    def mode(self) -> int:
+        return _lib.lib().mktfhe_get_mode(self._h)
+
+    # -- hot path ---------------------------------------------------------------------------------
+    def _batchify(self, c):
+        c = np.ascontiguousarray(c, dtype=np.uint32)
+        single = c.ndim == 1
+        if single:
+            c = c[None, :]
+        if c.shape[1] != self.params.lwe_words:
+            raise ValueError(f"ciphertext has {c.shape[1]} words, expected {self.params.lwe_words}")
+        return c, single
+
+    def gate(self, op: int, c1, c2):
+        """out = bootstrap(linear_op(c1, c2)): gate.jl:1-52.  Accepts one ciphertext or a batch [B, 1+n*k]."""
+        c1, single = self._batchify(c1)
+        c2, _ = self._batchify(c2)
+        if c1.shape != c2.shape:
+            raise ValueError("operand shapes differ")
+        out = np.empty_like(c1)
+        self._ck(_lib.lib().mktfhe_gate_batch(self._h, op, _ptr(c1), _ptr(c2), _ptr(out), c1.shape[0]), "mktfhe_gate_batch")
+        return out[0] if single else out
+
+    def bootstrapping(self, c):
+        """bootstrapping!(ctxt, scheme): bootstrapping.jl:4-27 (returns the result instead of mutating)."""
+        c, single = self._batchify(c)
+        out = np.empty_like(c)
+        self._ck(_lib.lib().mktfhe_bootstrap_batch(self._h, _ptr(c), _ptr(out), c.shape[0]), "mktfhe_bootstrap_batch")
+        return out[0] if single else out
+
+    def gate_dev(self, op: int, in1_ptr: int, in2_ptr: int, out_ptr: int, batch: int):
+        """Device-pointer variant (no copies, asynchronous on the context stream)."""
+        self._ck(_lib.lib().mktfhe_gate_batch_dev(self._h, op, in1_ptr, in2_ptr, out_ptr, batch), "mktfhe_gate_batch_dev")
+
+    def sync(self):
+        self._ck(_lib.lib().mktfhe_sync(self._h), "mktfhe_sync")
+
+    @property
+    def stream(self) -> int:
+        return _lib.lib().mktfhe_stream(self._h) or 0
+
+    # -- parity hooks -----------------------------------------------------------------------------
+    @property
+    def torus_dtype(self):
+        return np.uint64 if self.params.torus_bits == 64 else np.uint32
+
+    def gate_linear(self, op, c1, c2):
+        c1, single = self._batchify(c1)
+        c2, _ = self._batchify(c2)
+        out = np.empty_like(c1)
+        self._ck(_lib.lib().mktfhe_gate_linear_batch(self._h, op, _ptr(c1), _ptr(c2), _ptr(out), c1.shape[0]), "gate_linear")
+        return out[0] if single else out
+
+    def modswitch(self, c):
+        c, single = self._batchify(c)
+        out = np.empty_like(c)
+        self._ck(_lib.lib().mktfhe_modswitch_batch(self._h, _ptr(c), _ptr(out), c.shape[0]), "modswitch")
+        return out[0] if single else out
+
+    def blindrotate(self, c):
+        c, single = self._batchify(c)
+        p = self.params
+        acc = np.empty((c.shape[0], p.k + 1, p.N), dtype=self.torus_dtype)
+        self._ck(_lib.lib().mktfhe_blindrotate_batch(self._h, _ptr(c), _ptr(acc), c.shape[0]), "blindrotate")
+        return acc[0] if single else acc
+
+    def phase1(self, c):
+        c, single = self._batchify(c)
+        p = self.params
+        R = 1 + (p.k - 1) * p.l_lev
+        lev = np.empty((c.shape[0], R, 2, p.H, 2), dtype=np.float64)
+        self._ck(_lib.lib().mktfhe_phase1_batch(self._h, _ptr(c), _ptr(lev), c.shape[0]), "phase1")
+        return lev[0] if single else lev
+
+    def keyswitch(self, acc):
+        p = self.params
+        acc = np.ascontiguousarray(acc, dtype=self.torus_dtype)
+        single = acc.ndim == 2
+        if single:
+            acc = acc[None]
+        out = np.empty((acc.shape[0], p.lwe_words), dtype=np.uint32)
+        self._ck(_lib.lib().mktfhe_keyswitch_batch(self._h, _ptr(acc), _ptr(out), acc.shape[0]), "keyswitch")
+        return out[0] if single else out
+
+    def cmux_step(self, party, idx, atilde, acc_rows):
+        rows = np.array(acc_rows, dtype=self.torus_dtype, order="C", copy=True)
+        at = np.ascontiguousarray(atilde, dtype=np.uint32)
+        assert rows.ndim == 3 and rows.shape[0] == at.shape[0]
+        self._ck(_lib.lib().mktfhe_cmux_step_batch(self._h, party, idx, _ptr(at), _ptr(rows), rows.shape[0]), "cmux_step")
+        return rows
+
+    def fft(self, polys):
+        polys = np.ascontiguousarray(polys)
+        bits = polys.dtype.itemsize * 8
+        out = np.empty((polys.shape[0], self.params.H, 2), dtype=np.float64)
+        self._ck(_lib.lib().mktfhe_fft_batch(self._h, bits, _ptr(polys), _ptr(out), polys.shape[0]), "fft")
+        return out
+
+    def ifft(self, spectra, bits):
+        spectra = np.ascontiguousarray(spectra, dtype=np.float64)
+        out = np.empty((spectra.shape[0], self.params.N), dtype=np.uint64 if bits == 64 else np.uint32)
+        self._ck(_lib.lib().mktfhe_ifft_batch(self._h, bits, _ptr(spectra), _ptr(out), spectra.shape[0]), "ifft")
+        return out
+
+    def decomp(self, polys, l, logB):
+        polys = np.ascontiguousarray(polys)
+        bits = polys.dtype.itemsize * 8
+        out = np.empty((polys.shape[0], l, self.params.N), dtype=polys.dtype)
+        self._ck(_lib.lib().mktfhe_decomp_batch(self._h, bits, l, logB, _ptr(polys), _ptr(out), polys.shape[0]), "decomp")
+        return out
+
+    # -- measurement ------------------------------------------------------------------------------
+    def last_stage_ms(self):
+        ms = (ctypes.c_float * 4)()
+        n = ctypes.c_int()
+        self._ck(_lib.lib().mktfhe_last_stage_ms(self._h, ms, ctypes.byref(n)), "last_stage_ms")
+        return dict(zip(STAGES, [float(x) for x in ms])), n.value
+
+    def dfma_peak_tflops(self) -> float:
+        v = ctypes.c_double()
+        self._ck(_lib.lib().mktfhe_measure_dfma_peak(self._h, ctypes.byref(v)), "dfma_peak")
+        return v.value
+
+
+def setup(keys: KeySet, device: int = 0, mode: int | None = None) -> Scheme:
+    """`scheme = setup(a, btk, params)` / `setup(params)`: create the device context and upload every party's keys."""
+    p = keys.params
+    s = Scheme(p, device)
+    for i, q in enumerate(keys.parties):
+        s.upload_party(i, q["brk"], q["ksk"], q["rlk"], q["pubb"])
+    if p.is_mk:
+        s.upload_common(keys.crs_fft)
+    s.finalize()
+    if mode is not None:
+        s.set_mode(mode)
+    return s
