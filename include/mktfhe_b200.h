@@ -73,7 +73,9 @@ int mktfhe_get_mode(const mktfhe_ctx *ctx);
 
 /* ---- one-time key upload --------------------------------------------------------------------- */
 /* Replaces: holding `btk[party]` in the scheme struct (scheme.jl:107-116,209-219,256-265,301-312).
- * rlk / pubb may be NULL for schemes that have none. party = 0 for CGGI / LMSS. */
+ * rlk / pubb may be NULL for schemes that have none. party = 0 for CGGI / LMSS.
+ * Sources may be host pointers or device pointers of any GPU (copied with cudaMemcpyDefault), so a key set
+ * that arrived by NCCL broadcast is uploaded without a host round trip. */
 int mktfhe_upload_party_key(mktfhe_ctx *ctx, int party, const double *brk, const double *rlk,
                             const double *pubb, const uint32_t *ksk);
 /* Replaces: `fft(a, ffter)` stored as scheme.a (scheme.jl:251,298,349). NULL for CGGI / LMSS. */

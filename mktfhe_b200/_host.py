@@ -55,15 +55,16 @@ def crs(p: Params, seed: int):
     return coeff, fft
 
 
-def party_keygen(p: Params, seed: int, party: int, crs_coeff, nthreads: int = 0, want_ksk: bool = True):
+def party_keygen(p: Params, seed: int, party: int, crs_coeff, nthreads: int = 0, want_ksk: bool = True,
+                 want_eval: bool = True):
     cp = p.c_struct()
     out = {
         "lwekey": np.empty(p.n, dtype=np.uint32),
         "ringkey": np.empty(p.N, dtype=torus_dtype(p)),
-        "brk": np.empty((p.n, p.brk_polys, p.H, 2), dtype=np.float64),
-        "rlk": np.empty((p.l_uni, 3, p.H, 2), dtype=np.float64) if p.scheme in (3, 4) else None,
-        "pubb": np.empty((p.l_uni, p.H, 2), dtype=np.float64) if p.is_mk else None,
-        "ksk": np.empty((p.N, p.ksk_rows, p.f, p.n + 1), dtype=np.uint32) if want_ksk else None,
+        "brk": np.empty((p.n, p.brk_polys, p.H, 2), dtype=np.float64) if want_eval else None,
+        "rlk": np.empty((p.l_uni, 3, p.H, 2), dtype=np.float64) if (p.scheme in (3, 4) and want_eval) else None,
+        "pubb": np.empty((p.l_uni, p.H, 2), dtype=np.float64) if (p.is_mk and want_eval) else None,
+        "ksk": np.empty((p.N, p.ksk_rows, p.f, p.n + 1), dtype=np.uint32) if (want_ksk and want_eval) else None,
     }
     rc = lib().mktfhe_host_party_keygen(ctypes.byref(cp), seed, party, ptr(crs_coeff), ptr(out["lwekey"]),
                                         ptr(out["ringkey"]), ptr(out["brk"]), ptr(out["rlk"]), ptr(out["pubb"]),

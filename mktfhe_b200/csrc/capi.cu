@@ -254,7 +254,7 @@ void fft_tables_host(int N, std::vector<cplx> &psi, std::vector<cplx> &psiinv, s
 template <class T> int upload(mktfhe_ctx *ctx, T *&dst, const void *src, size_t bytes) {
     dfree(dst);
     CK(cudaMalloc(&dst, bytes));
-    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));   // host or device source (UVA)
     return 0;
 }
 

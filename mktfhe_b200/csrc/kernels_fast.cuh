@@ -1,17 +1,455 @@
-// kernels_fast.cuh -- FAST-mode phase 1 (placeholder until the register-resident kernel lands).
+// kernels_fast.cuh -- FAST-mode KMS phase 1 (the >= 98 % of the flops): register-resident FP64 transform.
+//
+// What it computes: /root/reference/src/tfhe/bootstrapping.jl:389-443 (phase_1 of KMS) -- per RLEV row and LWE
+// index: gadget-decompose (gsw.jl:86-96) -> forward transforms -> RGSW multiply-accumulate (polynomial.jl:105-108)
+// -> x (X^a - 1) -> inverse transforms -> round (arithmetic.jl:6-9) -> accumulate.  Integer stages are the
+// reference's exactly; floating-point stages use a different (mathematically equal) operation schedule:
+//
+//   * Transform: the reference twists by exp(i*pi*j/N) and then runs a negacyclic Cooley-Tukey network
+//     (fft.jl:57-63,105-155).  Both steps together evaluate c(Y) = sum (p_j - i*p_{j+H}) Y^j at the roots of
+//     Y^H + i, in bit-reversed order.  Here one radix-2 network does that directly: node (s, i) of the product
+//     tree Y^(H/2^s) - rho(s,i), rho(0,0) = -i, splits with twiddle sqrt(rho(s,i)).  No twist pass, the
+//     stage-1..4 twiddles are thread-invariant (constant bank), siblings differ by a factor -i, and slot n
+//     holds the same evaluation point as the reference's slot n, so keys need no slot permutation.
+//   * One unit = one (gate, party, row) = 64 threads x 16 points; passes of 4 + 4 + 2 stages in registers,
+//     two shared-memory exchanges per transform with XOR swizzles (bank-conflict free for 16-byte accesses).
+//   * Forward butterfly (t + w*u, t - w*u) in 6 FMA-pipe instructions: hi = 2t - lo.
+//   * The 2 x 16 complex accumulators of the RGSW product stay in registers across the 2*l digit transforms;
+//     bootstrapping-key polynomials are read straight from L2 with 16-byte coalesced loads in "thread order"
+//     ([e][t] = slot 16t + e), each value used once per unit.
+//   * (X^a - 1)/H is rebuilt per slot from two small tables: exp(-i*pi*(4*brv6(t)+1)*a/N) (per thread) times a
+//     16th root of unity (per register slot); the 1/H of the inverse transform rides on it.
 #pragma once
 #include <string>
 #include <vector>
 #include "common.cuh"
 #include "../../include/mktfhe_params.h"
 
-struct FastKeys { int dummy = 0; };
-static inline bool fast_supported(const mktfhe_params &) { return false; }
-static inline void fast_free(FastKeys &) {}
-static inline int fast_build(FastKeys &, const mktfhe_params &, const std::vector<cplx *> &, cudaStream_t, std::string &) { return 0; }
-static inline int fast_phase1(FastKeys &, const mktfhe_params &, const uint32_t *, cplx *, size_t, cudaStream_t, int *, std::string &err) {
-    err = "FAST mode not built"; return -1;
+namespace fast {
+
+constexpr int H = 1024, N = 2048, UT = 64, U = 4, CTA = UT * U;
+
+__constant__ double2 c_tw1[16];      // TW[1..15]: stages 1..4 (index 2^s + i), entry 0 unused
+__constant__ double2 c_e16[16];      // exp(-i*pi*j/8)
+
+struct Tables {
+    const cplx *tw;        // [1024] TW[2^s + i] = sqrt(rho(s, i)), s = 0..9
+    const cplx *tw9e;      // [256]  TW[512 + 2i]
+    const cplx *emono;     // [4096] exp(-i*pi*m/2048) / H
+};
+
+// ---- butterflies -------------------------------------------------------------------------------------
+// forward: (a, b) -> (a + w*b, a - w*b); 6 instructions (hi = 2a - lo)
+__device__ __forceinline__ void bf(cplx &a, cplx &b, const cplx w) {
+    const double lx = fma(-w.y, b.y, fma(w.x, b.x, a.x));
+    const double ly = fma(w.y, b.x, fma(w.x, b.y, a.y));
+    b.x = fma(2.0, a.x, -lx); b.y = fma(2.0, a.y, -ly);
+    a.x = lx; a.y = ly;
 }
-static inline int fast_cmux_step(FastKeys &, const mktfhe_params &, int, int, const uint32_t *, void *, size_t, cudaStream_t, int *, std::string &err) {
-    err = "FAST mode not built"; return -1;
+// forward with twiddle -i*w (sibling node): w*b rotated by -i
+__device__ __forceinline__ void bf_mi(cplx &a, cplx &b, const cplx w) {
+    const double lx = fma(w.y, b.x, fma(w.x, b.y, a.x));        // a.x + Im(w*b)
+    const double ly = fma(w.y, b.y, fma(-w.x, b.x, a.y));       // a.y - Re(w*b)
+    b.x = fma(2.0, a.x, -lx); b.y = fma(2.0, a.y, -ly);
+    a.x = lx; a.y = ly;
+}
+// inverse (unscaled): (A, B) -> (A + B, (A - B) * conj(w))
+__device__ __forceinline__ void bi(cplx &a, cplx &b, const cplx w) {
+    const double dx = a.x - b.x, dy = a.y - b.y;
+    a.x += b.x; a.y += b.y;
+    b.x = fma(w.y, dy, w.x * dx);            // Re(d * conj(w)) = dx*wx + dy*wy
+    b.y = fma(-w.y, dx, w.x * dy);           // Im(d * conj(w)) = dy*wx - dx*wy
+}
+// inverse with twiddle -i*w: conj(-i*w) = i*conj(w)
+__device__ __forceinline__ void bi_mi(cplx &a, cplx &b, const cplx w) {
+    const double dx = a.x - b.x, dy = a.y - b.y;
+    a.x += b.x; a.y += b.y;
+    b.x = -fma(-w.y, dx, w.x * dy);          // Re(i*z) = -Im(z)
+    b.y = fma(w.y, dy, w.x * dx);            // Im(i*z) =  Re(z)
+}
+
+// ---- in-register passes over x[16] ---------------------------------------------------------------------
+// stages 1..4 (spans 512..64): element m of thread t is point t + 64m; twiddles TW[2^s + (m >> (4-s))]
+__device__ __forceinline__ void pass1_fwd(cplx (&x)[16]) {
+#pragma unroll
+    for (int m = 0; m < 8; m++) bf(x[m], x[m + 8], c_tw1[1]);
+#pragma unroll
+    for (int m = 0; m < 16; m++) if (!(m & 4)) { if (m & 8) bf_mi(x[m], x[m + 4], c_tw1[2]); else bf(x[m], x[m + 4], c_tw1[2]); }
+#pragma unroll
+    for (int m = 0; m < 16; m++) if (!(m & 2)) { if (m & 4) bf_mi(x[m], x[m + 2], c_tw1[4 + (m >> 3) * 2]); else bf(x[m], x[m + 2], c_tw1[4 + (m >> 3) * 2]); }
+#pragma unroll
+    for (int m = 0; m < 16; m += 2) { if (m & 2) bf_mi(x[m], x[m + 1], c_tw1[8 + (m >> 2) * 2]); else bf(x[m], x[m + 1], c_tw1[8 + (m >> 2) * 2]); }
+}
+__device__ __forceinline__ void pass1_inv(cplx (&x)[16]) {
+#pragma unroll
+    for (int m = 0; m < 16; m += 2) { if (m & 2) bi_mi(x[m], x[m + 1], c_tw1[8 + (m >> 2) * 2]); else bi(x[m], x[m + 1], c_tw1[8 + (m >> 2) * 2]); }
+#pragma unroll
+    for (int m = 0; m < 16; m++) if (!(m & 2)) { if (m & 4) bi_mi(x[m], x[m + 2], c_tw1[4 + (m >> 3) * 2]); else bi(x[m], x[m + 2], c_tw1[4 + (m >> 3) * 2]); }
+#pragma unroll
+    for (int m = 0; m < 16; m++) if (!(m & 4)) { if (m & 8) bi_mi(x[m], x[m + 4], c_tw1[2]); else bi(x[m], x[m + 4], c_tw1[2]); }
+#pragma unroll
+    for (int m = 0; m < 8; m++) bi(x[m], x[m + 8], c_tw1[1]);
+}
+// stages 5..8 inside 64-point block `blk`: element q of the thread is point 64*blk + o + 4q;
+// twiddles TW[2^(4+ss) + (blk << ss) + (q >> (4-ss))]; odd nodes come from their even sibling.
+__device__ __forceinline__ void pass2_fwd(cplx (&x)[16], const cplx *__restrict__ tw, int blk) {
+    const cplx w4 = tw[16 + blk], w5 = tw[32 + 2 * blk];
+    const cplx w6a = tw[64 + 4 * blk], w6b = tw[64 + 4 * blk + 2];
+    const cplx w7a = tw[128 + 8 * blk], w7b = tw[128 + 8 * blk + 2], w7c = tw[128 + 8 * blk + 4], w7d = tw[128 + 8 * blk + 6];
+#pragma unroll
+    for (int q = 0; q < 8; q++) bf(x[q], x[q + 8], w4);
+#pragma unroll
+    for (int q = 0; q < 16; q++) if (!(q & 4)) { if (q & 8) bf_mi(x[q], x[q + 4], w5); else bf(x[q], x[q + 4], w5); }
+#pragma unroll
+    for (int q = 0; q < 16; q++) if (!(q & 2)) {
+        const cplx w = (q & 8) ? w6b : w6a;
+        if (q & 4) bf_mi(x[q], x[q + 2], w); else bf(x[q], x[q + 2], w);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q += 2) {
+        const cplx w = (q >> 2) == 0 ? w7a : (q >> 2) == 1 ? w7b : (q >> 2) == 2 ? w7c : w7d;
+        if (q & 2) bf_mi(x[q], x[q + 1], w); else bf(x[q], x[q + 1], w);
+    }
+}
+__device__ __forceinline__ void pass2_inv(cplx (&x)[16], const cplx *__restrict__ tw, int blk) {
+    const cplx w4 = tw[16 + blk], w5 = tw[32 + 2 * blk];
+    const cplx w6a = tw[64 + 4 * blk], w6b = tw[64 + 4 * blk + 2];
+    const cplx w7a = tw[128 + 8 * blk], w7b = tw[128 + 8 * blk + 2], w7c = tw[128 + 8 * blk + 4], w7d = tw[128 + 8 * blk + 6];
+#pragma unroll
+    for (int q = 0; q < 16; q += 2) {
+        const cplx w = (q >> 2) == 0 ? w7a : (q >> 2) == 1 ? w7b : (q >> 2) == 2 ? w7c : w7d;
+        if (q & 2) bi_mi(x[q], x[q + 1], w); else bi(x[q], x[q + 1], w);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) if (!(q & 2)) {
+        const cplx w = (q & 8) ? w6b : w6a;
+        if (q & 4) bi_mi(x[q], x[q + 2], w); else bi(x[q], x[q + 2], w);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) if (!(q & 4)) { if (q & 8) bi_mi(x[q], x[q + 4], w5); else bi(x[q], x[q + 4], w5); }
+#pragma unroll
+    for (int q = 0; q < 8; q++) bi(x[q], x[q + 8], w4);
+}
+// stages 9, 10 on the four 4-point groups 16t + 4g .. +3 of thread t: nodes 4t+g (depth 8) and 2(4t+g)+{0,1}
+__device__ __forceinline__ void pass3_fwd(cplx (&x)[16], const cplx *__restrict__ tw8, const cplx *__restrict__ tw9e, int t) {
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const cplx w8 = tw8[4 * t + g], w9 = tw9e[4 * t + g];
+        if (g & 1) { bf_mi(x[4 * g], x[4 * g + 2], tw8[4 * t + g - 1]); bf_mi(x[4 * g + 1], x[4 * g + 3], tw8[4 * t + g - 1]); }
+        else { bf(x[4 * g], x[4 * g + 2], w8); bf(x[4 * g + 1], x[4 * g + 3], w8); }
+        bf(x[4 * g], x[4 * g + 1], w9);
+        bf_mi(x[4 * g + 2], x[4 * g + 3], w9);
+    }
+}
+__device__ __forceinline__ void pass3_inv(cplx (&x)[16], const cplx *__restrict__ tw8, const cplx *__restrict__ tw9e, int t) {
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const cplx w8 = tw8[4 * t + g], w9 = tw9e[4 * t + g];
+        bi(x[4 * g], x[4 * g + 1], w9);
+        bi_mi(x[4 * g + 2], x[4 * g + 3], w9);
+        if (g & 1) { bi_mi(x[4 * g], x[4 * g + 2], tw8[4 * t + g - 1]); bi_mi(x[4 * g + 1], x[4 * g + 3], tw8[4 * t + g - 1]); }
+        else { bi(x[4 * g], x[4 * g + 2], w8); bi(x[4 * g + 1], x[4 * g + 3], w8); }
+    }
+}
+
+__device__ __forceinline__ void unit_bar(int unit) { asm volatile("bar.sync %0, %1;" ::"r"(unit + 1), "r"(UT) : "memory"); }
+
+// exchange index swizzles (16-byte elements; a quarter-warp must hit 8 distinct 16-byte bank groups)
+__device__ __forceinline__ int sw1(int n) { return n ^ (((n >> 6) & 1) << 2); }
+__device__ __forceinline__ int sw2(int n) { return n ^ ((n >> 4) & 7); }
+
+// x (layout A: point t + 64m) -> pass 1..3 -> x (layout C: slot 16t + e)
+__device__ __forceinline__ void fft_fwd(cplx (&x)[16], cplx *xb, const cplx *tw2, const cplx *tw8, const cplx *tw9e, int t, int unit) {
+    pass1_fwd(x);
+    unit_bar(unit);                                              // previous readers of xb are done
+#pragma unroll
+    for (int m = 0; m < 16; m++) xb[sw1(t + 64 * m)] = x[m];
+    unit_bar(unit);
+    const int blk = t >> 2, o = t & 3;
+#pragma unroll
+    for (int q = 0; q < 16; q++) x[q] = xb[sw1(64 * blk + o + 4 * q)];
+    pass2_fwd(x, tw2, blk);
+    unit_bar(unit);
+#pragma unroll
+    for (int q = 0; q < 16; q++) xb[sw2(64 * blk + o + 4 * q)] = x[q];
+    unit_bar(unit);
+#pragma unroll
+    for (int e = 0; e < 16; e++) x[e] = xb[sw2(16 * t + e)];
+    pass3_fwd(x, tw8, tw9e, t);
+}
+// x (layout C) -> x (layout A), unscaled inverse
+__device__ __forceinline__ void fft_inv(cplx (&x)[16], cplx *xb, const cplx *tw2, const cplx *tw8, const cplx *tw9e, int t, int unit) {
+    pass3_inv(x, tw8, tw9e, t);
+    unit_bar(unit);
+#pragma unroll
+    for (int e = 0; e < 16; e++) xb[sw2(16 * t + e)] = x[e];
+    unit_bar(unit);
+    const int blk = t >> 2, o = t & 3;
+#pragma unroll
+    for (int q = 0; q < 16; q++) x[q] = xb[sw2(64 * blk + o + 4 * q)];
+    pass2_inv(x, tw2, blk);
+    unit_bar(unit);
+#pragma unroll
+    for (int q = 0; q < 16; q++) xb[sw1(64 * blk + o + 4 * q)] = x[q];
+    unit_bar(unit);
+#pragma unroll
+    for (int m = 0; m < 16; m++) x[m] = xb[sw1(t + 64 * m)];
+    pass1_inv(x);
+}
+
+// int32 -> double without the conversion pipe
+__device__ __forceinline__ double i2d(int32_t d) {
+    return __hiloint2double(0x43300000, (int)((uint32_t)d ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
+}
+// x mod 2^64 as uint64, rounding toward -inf like `native` (arithmetic.jl:6-9)
+__device__ __forceinline__ uint64_t d2torus(double x) {
+    const double q = fma(x, 5.421010862427522e-20, 6755399441055744.0) - 6755399441055744.0;   // rint(x / 2^64)
+    const double y = fma(-18446744073709551616.0, q, x);
+    return (uint64_t)__double2ll_rd(y);
+}
+
+struct Args {
+    const uint32_t *tilde;        // [B][lwe_words] (phase 1) / [units] rotations (step mode)
+    const cplx *const *brk;       // [k] FAST-layout keys: [idx][dg][comp][e][t]
+    Tables tb;
+    cplx *lev_out;                // [B][R][2][H], reference slot order
+    uint64_t *acc_io;             // step mode: [units][2][N]
+    int step_mode, step_party, step_idx;
+    int n, k, l, logB, l_lev, logB_lev, R, lwe_words;
+    size_t units;
+};
+
+constexpr size_t SMEM_UNIT = (size_t)2 * N * 8 + (size_t)H * 16;              // acc b, a + exchange buffer
+constexpr size_t SMEM_BYTES = U * SMEM_UNIT + (size_t)(256 + 256 + 256) * 16;  // + tw2, tw8, tw9e
+
+__global__ void __launch_bounds__(CTA, 1) k_phase1(const Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, unit_l = tid / UT, t = tid % UT;
+    cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + U * SMEM_UNIT), *tw8 = tw2 + 256, *tw9e = tw8 + 256;
+    for (int i = tid; i < 256; i += CTA) { tw2[i] = a.tb.tw[i]; tw8[i] = a.tb.tw[256 + i]; tw9e[i] = a.tb.tw9e[i]; }
+    uint64_t *accb = reinterpret_cast<uint64_t *>(smem_raw + unit_l * SMEM_UNIT), *acca = accb + N;
+    cplx *xb = reinterpret_cast<cplx *>(accb + 2 * N);
+    __syncthreads();
+
+    const size_t unit = (size_t)blockIdx.x * U + unit_l;
+    const bool live = unit < a.units;            // dead units still take part in nothing: they own their barrier id
+    if (!live) return;
+
+    int gate, party, row = 0;
+    if (!a.step_mode) {
+        gate = (int)(unit / a.R);
+        const int r = (int)(unit % a.R);
+        party = r == 0 ? 0 : 1 + (r - 1) / a.l_lev;
+        row = r == 0 ? 0 : (r - 1) % a.l_lev;
+#pragma unroll
+        for (int m = 0; m < 32; m++) { accb[t + 64 * m] = 0; acca[t + 64 * m] = 0; }
+        if (t == 0) accb[0] = (uint64_t)1 << (64 - (row + 1) * a.logB_lev);          // bootstrapping.jl:402-408
+    } else {
+        gate = (int)unit; party = a.step_party;
+        const uint64_t *src = a.acc_io + unit * 2 * N;
+#pragma unroll
+        for (int m = 0; m < 32; m++) { accb[t + 64 * m] = src[t + 64 * m]; acca[t + 64 * m] = src[N + t + 64 * m]; }
+    }
+    // thread-private ownership: thread t only ever touches coefficients t + 64m (+H) of its unit, so no barrier is
+    // needed around the accumulator itself.
+
+    const int l = a.l, logB = a.logB;
+    const int bit = 64 - l * logB;
+    uint64_t off = 0;                                  // balanced digits in one shot: add B/2 at every digit position
+    for (int j = 0; j < l; j++) off |= (uint64_t)1 << (j * logB + logB - 1);
+    const uint32_t mask = (1u << logB) - 1;
+    const int32_t halfB = 1 << (logB - 1);
+    const cplx *brk = a.brk[party];
+    const size_t per_idx = (size_t)4 * l * H;
+    const uint32_t *at_src = a.step_mode ? a.tilde + unit : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
+    const int nsteps = a.step_mode ? 1 : a.n;
+    int brv6t = (int)(__brev((unsigned)t) >> 26);
+
+    for (int step = 0; step < nsteps; step++) {
+        const uint32_t at = at_src[a.step_mode ? 0 : step];
+        if (at == 0) continue;                                                        // :413
+        const int idx = a.step_mode ? a.step_idx : step;
+        const cplx *kidx = brk + (size_t)idx * per_idx + t;
+
+        cplx tb_[16], ta_[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) tb_[e] = ta_[e] = make_double2(0.0, 0.0);
+
+        for (int dg = 0; dg < 2 * l; dg++) {
+            const uint64_t *src = dg < l ? accb : acca;
+            const int sh = (l - 1 - (dg < l ? dg : dg - l)) * logB;
+            cplx x[16];
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const uint64_t v0 = src[t + 64 * m], v1 = src[t + 64 * m + H];
+                // divbits (arithmetic.jl:23-27) then digit extraction (gsw.jl:86-96, closed form of the carry chain)
+                const uint64_t a0 = (v0 >> bit) + ((v0 >> (bit - 1)) & 1) + off;
+                const uint64_t a1 = (v1 >> bit) + ((v1 >> (bit - 1)) & 1) + off;
+                const int32_t d0 = (int32_t)((uint32_t)(a0 >> sh) & mask) - halfB;
+                const int32_t d1 = (int32_t)((uint32_t)(a1 >> sh) & mask) - halfB;
+                x[m] = make_double2(i2d(d0), i2d(-d1));                              // signed(p_j) - im*signed(p_{j+H})
+            }
+            fft_fwd(x, xb, tw2, tw8, tw9e, t, unit_l);
+            const cplx *kb = kidx + (size_t)(dg * 2) * H, *ka = kb + H;
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const cplx wb = __ldg(kb + e * UT), wa = __ldg(ka + e * UT);
+                tb_[e] = cmac_f(tb_[e], x[e], wb);
+                ta_[e] = cmac_f(ta_[e], x[e], wa);
+            }
+        }
+        // (X^a - 1) / H per slot: slot n = 16t + e evaluates at exp(-i*pi*(4*brv10(n)+1)/N), brv10(n) = 64*brv4(e) + brv6(t)
+        const cplx m1 = __ldg(&a.tb.emono[((4 * brv6t + 1) * at) & 4095]);
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
+            cplx mo = cmul_f(m1, c_e16[(at * b4) & 15]);
+            mo.x -= 1.0 / H;
+            tb_[e] = cmul_f(mo, tb_[e]);
+            ta_[e] = cmul_f(mo, ta_[e]);
+        }
+        fft_inv(tb_, xb, tw2, tw8, tw9e, t, unit_l);
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            accb[t + 64 * m] += d2torus(tb_[m].x);
+            accb[t + 64 * m + H] += d2torus(-tb_[m].y);
+        }
+        fft_inv(ta_, xb, tw2, tw8, tw9e, t, unit_l);
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            acca[t + 64 * m] += d2torus(ta_[m].x);
+            acca[t + 64 * m + H] += d2torus(-ta_[m].y);
+        }
+    }
+
+    if (!a.step_mode) {            // fftto!(tacc, acc): bootstrapping.jl:441 -- full-width coefficients
+        cplx *out = a.lev_out + unit * 2 * H;
+#pragma unroll 1
+        for (int c = 0; c < 2; c++) {
+            const uint64_t *src = c == 0 ? accb : acca;
+            cplx x[16];
+#pragma unroll
+            for (int m = 0; m < 16; m++)
+                x[m] = make_double2(__ll2double_rn((long long)src[t + 64 * m]),
+                                    __ll2double_rn((long long)((uint64_t)0 - src[t + 64 * m + H])));
+            fft_fwd(x, xb, tw2, tw8, tw9e, t, unit_l);
+#pragma unroll
+            for (int e = 0; e < 16; e++) out[(size_t)c * H + 16 * t + e] = x[e];
+        }
+    } else {
+        uint64_t *dst = a.acc_io + unit * 2 * N;
+#pragma unroll
+        for (int m = 0; m < 32; m++) { dst[t + 64 * m] = accb[t + 64 * m]; dst[N + t + 64 * m] = acca[t + 64 * m]; }
+    }
+}
+
+// reference slot order [poly][16t + e] -> thread order [poly][e][t]
+__global__ void k_permute_brk(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= polys * H) return;
+    const size_t p = i / H;
+    const int r = (int)(i % H), e = r / UT, t = r % UT;
+    out[i] = in[p * H + 16 * t + e];
+}
+
+}  // namespace fast
+
+struct FastKeys {
+    std::vector<cplx *> brk;        // per party, FAST layout
+    cplx **d_brk = nullptr;
+    cplx *tw = nullptr, *tw9e = nullptr, *emono = nullptr;
+    bool built = false;
+};
+
+static inline bool fast_supported(const mktfhe_params &p) { return p.scheme == MKTFHE_KMS && p.N == 2048; }
+
+static inline void fast_free(FastKeys &f) {
+    for (auto &q : f.brk) if (q) cudaFree(q);
+    f.brk.clear();
+    if (f.d_brk) cudaFree(f.d_brk);
+    if (f.tw) cudaFree(f.tw);
+    if (f.tw9e) cudaFree(f.tw9e);
+    if (f.emono) cudaFree(f.emono);
+    f.d_brk = nullptr; f.tw = f.tw9e = f.emono = nullptr; f.built = false;
+}
+
+#define FCK(call)                                                                        \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return MKTFHE_ERR_CUDA_; } \
+    } while (0)
+#define MKTFHE_ERR_CUDA_ (-2)
+
+// Twiddles sqrt(rho(s, i)) = exp(-i*pi*theta(s,i)/2): theta(0,0) = 1/2, theta(s+1, 2i+b) = theta(s,i)/2 + b.
+static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vector<cplx *> &brk_ref, cudaStream_t stream, std::string &err) {
+    using namespace fast;
+    fast_free(f);
+    std::vector<__float128> theta(1, (__float128)0.5);
+    std::vector<cplx> tw(1024, make_double2(0.0, 0.0)), tw9e(256), emono(4096), e16(16), tw1(16, make_double2(0.0, 0.0));
+    const __float128 pi = acosq((__float128)-1);
+    for (int s = 0; s < 10; s++) {
+        std::vector<__float128> nxt(theta.size() * 2);
+        for (size_t i = 0; i < theta.size(); i++) {
+            const __float128 ang = pi * theta[i] / 2;
+            tw[((size_t)1 << s) + i] = make_double2((double)cosq(ang), (double)-sinq(ang));
+            nxt[2 * i] = theta[i] / 2; nxt[2 * i + 1] = theta[i] / 2 + 1;
+        }
+        theta.swap(nxt);
+    }
+    for (int i = 0; i < 256; i++) tw9e[i] = tw[512 + 2 * i];
+    for (int m = 0; m < 4096; m++) {
+        const __float128 ang = pi * m / 2048;
+        emono[m] = make_double2((double)(cosq(ang) / H), (double)(-sinq(ang) / H));
+    }
+    for (int j = 0; j < 16; j++) { const __float128 ang = pi * j / 8; e16[j] = make_double2((double)cosq(ang), (double)-sinq(ang)); }
+    for (int i = 1; i < 16; i++) tw1[i] = tw[i];
+    FCK(cudaMalloc(&f.tw, sizeof(cplx) * 1024));
+    FCK(cudaMalloc(&f.tw9e, sizeof(cplx) * 256));
+    FCK(cudaMalloc(&f.emono, sizeof(cplx) * 4096));
+    FCK(cudaMemcpy(f.tw, tw.data(), sizeof(cplx) * 1024, cudaMemcpyHostToDevice));
+    FCK(cudaMemcpy(f.tw9e, tw9e.data(), sizeof(cplx) * 256, cudaMemcpyHostToDevice));
+    FCK(cudaMemcpy(f.emono, emono.data(), sizeof(cplx) * 4096, cudaMemcpyHostToDevice));
+    FCK(cudaMemcpyToSymbol(c_tw1, tw1.data(), sizeof(cplx) * 16));
+    FCK(cudaMemcpyToSymbol(c_e16, e16.data(), sizeof(cplx) * 16));
+    const size_t polys = (size_t)p.n * 4 * p.l_gsw;
+    f.brk.assign(brk_ref.size(), nullptr);
+    for (size_t i = 0; i < brk_ref.size(); i++) {
+        FCK(cudaMalloc(&f.brk[i], polys * H * sizeof(cplx)));
+        k_permute_brk<<<(unsigned)((polys * H + 255) / 256), 256, 0, stream>>>(brk_ref[i], f.brk[i], polys);
+        FCK(cudaGetLastError());
+    }
+    FCK(cudaMalloc(&f.d_brk, sizeof(cplx *) * f.brk.size()));
+    FCK(cudaMemcpy(f.d_brk, f.brk.data(), sizeof(cplx *) * f.brk.size(), cudaMemcpyHostToDevice));
+    FCK(cudaFuncSetAttribute(k_phase1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    f.built = true;
+    return 0;
+}
+
+static inline int fast_launch(FastKeys &f, const mktfhe_params &p, fast::Args a, cudaStream_t stream, int *launches, std::string &err) {
+    using namespace fast;
+    if (!f.built) { err = "FAST keys not built"; return -3; }
+    a.brk = f.d_brk; a.tb = Tables{f.tw, f.tw9e, f.emono};
+    a.n = p.n; a.k = p.k; a.l = p.l_gsw; a.logB = p.logB_gsw; a.l_lev = p.l_lev; a.logB_lev = p.logB_lev;
+    a.R = 1 + (p.k - 1) * p.l_lev; a.lwe_words = (int)mktfhe_lwe_words(&p);
+    const unsigned grid = (unsigned)((a.units + U - 1) / U);
+    k_phase1<<<grid, CTA, SMEM_BYTES, stream>>>(a);
+    if (launches) (*launches)++;
+    FCK(cudaGetLastError());
+    return 0;
+}
+
+static inline int fast_phase1(FastKeys &f, const mktfhe_params &p, const uint32_t *tilde, cplx *lev, size_t gates,
+                              cudaStream_t stream, int *launches, std::string &err) {
+    fast::Args a{};
+    a.tilde = tilde; a.lev_out = lev; a.step_mode = 0;
+    a.units = gates * (size_t)(1 + (p.k - 1) * p.l_lev);
+    return fast_launch(f, p, a, stream, launches, err);
+}
+
+static inline int fast_cmux_step(FastKeys &f, const mktfhe_params &p, int party, int idx, const uint32_t *atilde, void *rows,
+                                 size_t batch, cudaStream_t stream, int *launches, std::string &err) {
+    fast::Args a{};
+    a.tilde = atilde; a.acc_io = (uint64_t *)rows; a.step_mode = 1; a.step_party = party; a.step_idx = idx;
+    a.units = batch;
+    return fast_launch(f, p, a, stream, launches, err);
 }

@@ -17,14 +17,16 @@ from .params import Params
 class KeySet:
     """All parties' secret and evaluation keys for one parameter set, generated from a seed."""
 
-    def __init__(self, params: Params, seed: int = 0x4D4B5446, nthreads: int = 0, want_ksk: bool = True):
+    def __init__(self, params: Params, seed: int = 0x4D4B5446, nthreads: int = 0, want_ksk: bool = True,
+                 secret_only: bool = False):
         self.params = p = params
         self.seed = seed
         self.crs_coeff = self.crs_fft = None
         if p.is_mk:
             self.crs_coeff, self.crs_fft = _host.crs(p, seed)
         nparties = p.k if p.is_mk else 1
-        self.parties = [_host.party_keygen(p, seed, i, self.crs_coeff, nthreads, want_ksk) for i in range(nparties)]
+        self.parties = [_host.party_keygen(p, seed, i, self.crs_coeff, nthreads, want_ksk, not secret_only)
+                        for i in range(nparties)]
         self.lwekeys = np.ascontiguousarray(np.stack([q["lwekey"] for q in self.parties]))   # [k][n]
 
     # flat views -------------------------------------------------------------------------

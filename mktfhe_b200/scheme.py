@@ -61,8 +61,13 @@ class Scheme:
         self._ck(_lib.lib().mktfhe_upload_party_key(self._h, party, _ptr(brk), _ptr(rlk), _ptr(pubb), _ptr(ksk)),
                  "mktfhe_upload_party_key")
 
+    def upload_party_ptr(self, party: int, brk: int, ksk: int, rlk: int | None = None, pubb: int | None = None):
+        """Raw-pointer upload (host or device addresses), e.g. of tensors received by NCCL broadcast."""
+        self._ck(_lib.lib().mktfhe_upload_party_key(self._h, party, brk, rlk, pubb, ksk), "mktfhe_upload_party_key")
+
     def upload_common(self, crs_fft):
-        self._ck(_lib.lib().mktfhe_upload_common(self._h, _ptr(crs_fft)), "mktfhe_upload_common")
+        ptr = crs_fft if isinstance(crs_fft, int) or crs_fft is None else _ptr(crs_fft)
+        self._ck(_lib.lib().mktfhe_upload_common(self._h, ptr), "mktfhe_upload_common")
 
     def finalize(self):
         self._ck(_lib.lib().mktfhe_finalize_keys(self._h), "mktfhe_finalize_keys")
