@@ -33,8 +33,9 @@ __constant__ double2 c_tw1[16];      // TW[1..15]: stages 1..4 (index 2^s + i), 
 __constant__ double2 c_e16[16];      // exp(-i*pi*j/8)
 
 struct Tables {
-    const cplx *tw;        // [1024] TW[2^s + i] = sqrt(rho(s, i)), s = 0..9
-    const cplx *tw9e;      // [256]  TW[512 + 2i]
+    const cplx *t2;        // [8][16]  pass-2 twiddles per 64-point block: w4, w5, w6a, w6b, w7a..w7d (even nodes)
+    const cplx *t8;        // [2][64]  TW[256 + 4t + g], g = 0, 2
+    const cplx *t9;        // [4][64]  TW[512 + 2(4t + g)], g = 0..3
     const cplx *emono;     // [4096] exp(-i*pi*m/2048) / H
 };
 
@@ -93,9 +94,9 @@ __device__ __forceinline__ void pass1_inv(cplx (&x)[16]) {
 // stages 5..8 inside 64-point block `blk`: element q of the thread is point 64*blk + o + 4q;
 // twiddles TW[2^(4+ss) + (blk << ss) + (q >> (4-ss))]; odd nodes come from their even sibling.
 __device__ __forceinline__ void pass2_fwd(cplx (&x)[16], const cplx *__restrict__ tw, int blk) {
-    const cplx w4 = tw[16 + blk], w5 = tw[32 + 2 * blk];
-    const cplx w6a = tw[64 + 4 * blk], w6b = tw[64 + 4 * blk + 2];
-    const cplx w7a = tw[128 + 8 * blk], w7b = tw[128 + 8 * blk + 2], w7c = tw[128 + 8 * blk + 4], w7d = tw[128 + 8 * blk + 6];
+    const cplx w4 = tw[blk], w5 = tw[16 + blk];
+    const cplx w6a = tw[32 + blk], w6b = tw[48 + blk];
+    const cplx w7a = tw[64 + blk], w7b = tw[80 + blk], w7c = tw[96 + blk], w7d = tw[112 + blk];
 #pragma unroll
     for (int q = 0; q < 8; q++) bf(x[q], x[q + 8], w4);
 #pragma unroll
@@ -112,9 +113,9 @@ __device__ __forceinline__ void pass2_fwd(cplx (&x)[16], const cplx *__restrict_
     }
 }
 __device__ __forceinline__ void pass2_inv(cplx (&x)[16], const cplx *__restrict__ tw, int blk) {
-    const cplx w4 = tw[16 + blk], w5 = tw[32 + 2 * blk];
-    const cplx w6a = tw[64 + 4 * blk], w6b = tw[64 + 4 * blk + 2];
-    const cplx w7a = tw[128 + 8 * blk], w7b = tw[128 + 8 * blk + 2], w7c = tw[128 + 8 * blk + 4], w7d = tw[128 + 8 * blk + 6];
+    const cplx w4 = tw[blk], w5 = tw[16 + blk];
+    const cplx w6a = tw[32 + blk], w6b = tw[48 + blk];
+    const cplx w7a = tw[64 + blk], w7b = tw[80 + blk], w7c = tw[96 + blk], w7d = tw[112 + blk];
 #pragma unroll
     for (int q = 0; q < 16; q += 2) {
         const cplx w = (q >> 2) == 0 ? w7a : (q >> 2) == 1 ? w7b : (q >> 2) == 2 ? w7c : w7d;
@@ -134,8 +135,8 @@ __device__ __forceinline__ void pass2_inv(cplx (&x)[16], const cplx *__restrict_
 __device__ __forceinline__ void pass3_fwd(cplx (&x)[16], const cplx *__restrict__ tw8, const cplx *__restrict__ tw9e, int t) {
 #pragma unroll
     for (int g = 0; g < 4; g++) {
-        const cplx w8 = tw8[4 * t + g], w9 = tw9e[4 * t + g];
-        if (g & 1) { bf_mi(x[4 * g], x[4 * g + 2], tw8[4 * t + g - 1]); bf_mi(x[4 * g + 1], x[4 * g + 3], tw8[4 * t + g - 1]); }
+        const cplx w8 = tw8[(g >> 1) * UT + t], w9 = tw9e[g * UT + t];
+        if (g & 1) { bf_mi(x[4 * g], x[4 * g + 2], w8); bf_mi(x[4 * g + 1], x[4 * g + 3], w8); }
         else { bf(x[4 * g], x[4 * g + 2], w8); bf(x[4 * g + 1], x[4 * g + 3], w8); }
         bf(x[4 * g], x[4 * g + 1], w9);
         bf_mi(x[4 * g + 2], x[4 * g + 3], w9);
@@ -144,37 +145,42 @@ __device__ __forceinline__ void pass3_fwd(cplx (&x)[16], const cplx *__restrict_
 __device__ __forceinline__ void pass3_inv(cplx (&x)[16], const cplx *__restrict__ tw8, const cplx *__restrict__ tw9e, int t) {
 #pragma unroll
     for (int g = 0; g < 4; g++) {
-        const cplx w8 = tw8[4 * t + g], w9 = tw9e[4 * t + g];
+        const cplx w8 = tw8[(g >> 1) * UT + t], w9 = tw9e[g * UT + t];
         bi(x[4 * g], x[4 * g + 1], w9);
         bi_mi(x[4 * g + 2], x[4 * g + 3], w9);
-        if (g & 1) { bi_mi(x[4 * g], x[4 * g + 2], tw8[4 * t + g - 1]); bi_mi(x[4 * g + 1], x[4 * g + 3], tw8[4 * t + g - 1]); }
+        if (g & 1) { bi_mi(x[4 * g], x[4 * g + 2], w8); bi_mi(x[4 * g + 1], x[4 * g + 3], w8); }
         else { bi(x[4 * g], x[4 * g + 2], w8); bi(x[4 * g + 1], x[4 * g + 3], w8); }
     }
 }
 
 __device__ __forceinline__ void unit_bar(int unit) { asm volatile("bar.sync %0, %1;" ::"r"(unit + 1), "r"(UT) : "memory"); }
 
-// exchange index swizzles (16-byte elements; a quarter-warp must hit 8 distinct 16-byte bank groups)
-__device__ __forceinline__ int sw1(int n) { return n ^ (((n >> 6) & 1) << 2); }
-__device__ __forceinline__ int sw2(int n) { return n ^ ((n >> 4) & 7); }
+// Exchange layouts (16-byte elements; a quarter-warp must hit 8 distinct 16-byte bank groups).  Additive padding
+// keeps every access at [per-thread base + compile-time offset]:
+//   exchange 1: pos1(n) = n + 4*(n >> 6)   (64-point blocks skewed by 4)
+//   exchange 2: pos2(n) = n + (n >> 4)     (16-slot runs skewed by 1)
+constexpr int XB_LEN = H + 64;
+__device__ __forceinline__ constexpr int p1(int n) { return n + 4 * (n >> 6); }
+__device__ __forceinline__ constexpr int p2(int n) { return n + (n >> 4); }
 
 // x (layout A: point t + 64m) -> pass 1..3 -> x (layout C: slot 16t + e)
 __device__ __forceinline__ void fft_fwd(cplx (&x)[16], cplx *xb, const cplx *tw2, const cplx *tw8, const cplx *tw9e, int t, int unit) {
     pass1_fwd(x);
     unit_bar(unit);                                              // previous readers of xb are done
 #pragma unroll
-    for (int m = 0; m < 16; m++) xb[sw1(t + 64 * m)] = x[m];
+    for (int m = 0; m < 16; m++) xb[t + 68 * m] = x[m];                       // pos1(t + 64m)
     unit_bar(unit);
     const int blk = t >> 2, o = t & 3;
+    cplx *xq = xb + 68 * blk + o;
 #pragma unroll
-    for (int q = 0; q < 16; q++) x[q] = xb[sw1(64 * blk + o + 4 * q)];
+    for (int q = 0; q < 16; q++) x[q] = xq[4 * q];                            // pos1(64blk + o + 4q)
     pass2_fwd(x, tw2, blk);
     unit_bar(unit);
 #pragma unroll
-    for (int q = 0; q < 16; q++) xb[sw2(64 * blk + o + 4 * q)] = x[q];
+    for (int q = 0; q < 16; q++) xq[4 * q + (q >> 2)] = x[q];                 // pos2(64blk + o + 4q)
     unit_bar(unit);
 #pragma unroll
-    for (int e = 0; e < 16; e++) x[e] = xb[sw2(16 * t + e)];
+    for (int e = 0; e < 16; e++) x[e] = xb[17 * t + e];                       // pos2(16t + e)
     pass3_fwd(x, tw8, tw9e, t);
 }
 // x (layout C) -> x (layout A), unscaled inverse
@@ -182,18 +188,19 @@ __device__ __forceinline__ void fft_inv(cplx (&x)[16], cplx *xb, const cplx *tw2
     pass3_inv(x, tw8, tw9e, t);
     unit_bar(unit);
 #pragma unroll
-    for (int e = 0; e < 16; e++) xb[sw2(16 * t + e)] = x[e];
+    for (int e = 0; e < 16; e++) xb[17 * t + e] = x[e];
     unit_bar(unit);
     const int blk = t >> 2, o = t & 3;
+    cplx *xq = xb + 68 * blk + o;
 #pragma unroll
-    for (int q = 0; q < 16; q++) x[q] = xb[sw2(64 * blk + o + 4 * q)];
+    for (int q = 0; q < 16; q++) x[q] = xq[4 * q + (q >> 2)];
     pass2_inv(x, tw2, blk);
     unit_bar(unit);
 #pragma unroll
-    for (int q = 0; q < 16; q++) xb[sw1(64 * blk + o + 4 * q)] = x[q];
+    for (int q = 0; q < 16; q++) xq[4 * q] = x[q];
     unit_bar(unit);
 #pragma unroll
-    for (int m = 0; m < 16; m++) x[m] = xb[sw1(t + 64 * m)];
+    for (int m = 0; m < 16; m++) x[m] = xb[t + 68 * m];
     pass1_inv(x);
 }
 
@@ -219,14 +226,14 @@ struct Args {
     size_t units;
 };
 
-constexpr size_t SMEM_UNIT = (size_t)2 * N * 8 + (size_t)H * 16;              // acc b, a + exchange buffer
-constexpr size_t SMEM_BYTES = U * SMEM_UNIT + (size_t)(256 + 256 + 256) * 16;  // + tw2, tw8, tw9e
+constexpr size_t SMEM_UNIT = (size_t)2 * N * 8 + (size_t)XB_LEN * 16;         // acc b, a + exchange buffer
+constexpr size_t SMEM_BYTES = U * SMEM_UNIT + (size_t)(128 + 128 + 256) * 16;  // + t2, t8, t9
 
 __global__ void __launch_bounds__(CTA, 1) k_phase1(const Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, unit_l = tid / UT, t = tid % UT;
-    cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + U * SMEM_UNIT), *tw8 = tw2 + 256, *tw9e = tw8 + 256;
-    for (int i = tid; i < 256; i += CTA) { tw2[i] = a.tb.tw[i]; tw8[i] = a.tb.tw[256 + i]; tw9e[i] = a.tb.tw9e[i]; }
+    cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + U * SMEM_UNIT), *tw8 = tw2 + 128, *tw9e = tw8 + 128;
+    for (int i = tid; i < 256; i += CTA) { if (i < 128) { tw2[i] = a.tb.t2[i]; tw8[i] = a.tb.t8[i]; } tw9e[i] = a.tb.t9[i]; }
     uint64_t *accb = reinterpret_cast<uint64_t *>(smem_raw + unit_l * SMEM_UNIT), *acca = accb + N;
     cplx *xb = reinterpret_cast<cplx *>(accb + 2 * N);
     __syncthreads();
@@ -255,10 +262,13 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1(const Args a) {
 
     const int l = a.l, logB = a.logB;
     const int bit = 64 - l * logB;
-    uint64_t off = 0;                                  // balanced digits in one shot: add B/2 at every digit position
-    for (int j = 0; j < l; j++) off |= (uint64_t)1 << (j * logB + logB - 1);
+    // divbits rounding (arithmetic.jl:23-27) and the balanced-digit carry chain (gsw.jl:86-96) in one 64-bit add:
+    // adding 2^(bit-1) rounds, adding B/2 at every digit position turns the carry chain into plain field extraction
+    // (field - B/2 is the balanced digit); everything is mod 2^64, i.e. mod 2^(l*logB) on the digits, like the reference.
+    uint64_t cadd = (uint64_t)1 << (bit - 1);
+    for (int j = 0; j < l; j++) cadd += (uint64_t)1 << (bit + j * logB + logB - 1);
     const uint32_t mask = (1u << logB) - 1;
-    const int32_t halfB = 1 << (logB - 1);
+    const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));       // 2^52 + B/2
     const cplx *brk = a.brk[party];
     const size_t per_idx = (size_t)4 * l * H;
     const uint32_t *at_src = a.step_mode ? a.tilde + unit : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
@@ -277,17 +287,14 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1(const Args a) {
 
         for (int dg = 0; dg < 2 * l; dg++) {
             const uint64_t *src = dg < l ? accb : acca;
-            const int sh = (l - 1 - (dg < l ? dg : dg - l)) * logB;
+            const int sh = bit + (l - 1 - (dg < l ? dg : dg - l)) * logB;
             cplx x[16];
 #pragma unroll
             for (int m = 0; m < 16; m++) {
-                const uint64_t v0 = src[t + 64 * m], v1 = src[t + 64 * m + H];
-                // divbits (arithmetic.jl:23-27) then digit extraction (gsw.jl:86-96, closed form of the carry chain)
-                const uint64_t a0 = (v0 >> bit) + ((v0 >> (bit - 1)) & 1) + off;
-                const uint64_t a1 = (v1 >> bit) + ((v1 >> (bit - 1)) & 1) + off;
-                const int32_t d0 = (int32_t)((uint32_t)(a0 >> sh) & mask) - halfB;
-                const int32_t d1 = (int32_t)((uint32_t)(a1 >> sh) & mask) - halfB;
-                x[m] = make_double2(i2d(d0), i2d(-d1));                              // signed(p_j) - im*signed(p_{j+H})
+                const uint64_t v0 = src[t + 64 * m] + cadd, v1 = src[t + 64 * m + H] + cadd;
+                const uint32_t f0 = (uint32_t)(v0 >> sh) & mask, f1 = (uint32_t)(v1 >> sh) & mask;
+                // signed(d_j) - im*signed(d_{j+H}); 2^52 + field is exact in the double's mantissa
+                x[m] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
             }
             fft_fwd(x, xb, tw2, tw8, tw9e, t, unit_l);
             const cplx *kb = kidx + (size_t)(dg * 2) * H, *ka = kb + H;
@@ -357,7 +364,7 @@ __global__ void k_permute_brk(const cplx *__restrict__ in, cplx *__restrict__ ou
 struct FastKeys {
     std::vector<cplx *> brk;        // per party, FAST layout
     cplx **d_brk = nullptr;
-    cplx *tw = nullptr, *tw9e = nullptr, *emono = nullptr;
+    cplx *t2 = nullptr, *t8 = nullptr, *t9 = nullptr, *emono = nullptr;
     bool built = false;
 };
 
@@ -367,10 +374,11 @@ static inline void fast_free(FastKeys &f) {
     for (auto &q : f.brk) if (q) cudaFree(q);
     f.brk.clear();
     if (f.d_brk) cudaFree(f.d_brk);
-    if (f.tw) cudaFree(f.tw);
-    if (f.tw9e) cudaFree(f.tw9e);
+    if (f.t2) cudaFree(f.t2);
+    if (f.t8) cudaFree(f.t8);
+    if (f.t9) cudaFree(f.t9);
     if (f.emono) cudaFree(f.emono);
-    f.d_brk = nullptr; f.tw = f.tw9e = f.emono = nullptr; f.built = false;
+    f.d_brk = nullptr; f.t2 = f.t8 = f.t9 = f.emono = nullptr; f.built = false;
 }
 
 #define FCK(call)                                                                        \
@@ -385,7 +393,7 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
     using namespace fast;
     fast_free(f);
     std::vector<__float128> theta(1, (__float128)0.5);
-    std::vector<cplx> tw(1024, make_double2(0.0, 0.0)), tw9e(256), emono(4096), e16(16), tw1(16, make_double2(0.0, 0.0));
+    std::vector<cplx> tw(1024, make_double2(0.0, 0.0)), t2(128), t8(128), t9(256), emono(4096), e16(16), tw1(16, make_double2(0.0, 0.0));
     const __float128 pi = acosq((__float128)-1);
     for (int s = 0; s < 10; s++) {
         std::vector<__float128> nxt(theta.size() * 2);
@@ -396,18 +404,28 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
         }
         theta.swap(nxt);
     }
-    for (int i = 0; i < 256; i++) tw9e[i] = tw[512 + 2 * i];
+    for (int blk = 0; blk < 16; blk++) {
+        t2[blk] = tw[16 + blk]; t2[16 + blk] = tw[32 + 2 * blk];
+        t2[32 + blk] = tw[64 + 4 * blk]; t2[48 + blk] = tw[64 + 4 * blk + 2];
+        for (int c = 0; c < 4; c++) t2[64 + 16 * c + blk] = tw[128 + 8 * blk + 2 * c];
+    }
+    for (int t = 0; t < 64; t++) {
+        t8[t] = tw[256 + 4 * t]; t8[64 + t] = tw[256 + 4 * t + 2];
+        for (int g = 0; g < 4; g++) t9[g * 64 + t] = tw[512 + 2 * (4 * t + g)];
+    }
     for (int m = 0; m < 4096; m++) {
         const __float128 ang = pi * m / 2048;
         emono[m] = make_double2((double)(cosq(ang) / H), (double)(-sinq(ang) / H));
     }
     for (int j = 0; j < 16; j++) { const __float128 ang = pi * j / 8; e16[j] = make_double2((double)cosq(ang), (double)-sinq(ang)); }
     for (int i = 1; i < 16; i++) tw1[i] = tw[i];
-    FCK(cudaMalloc(&f.tw, sizeof(cplx) * 1024));
-    FCK(cudaMalloc(&f.tw9e, sizeof(cplx) * 256));
+    FCK(cudaMalloc(&f.t2, sizeof(cplx) * 128));
+    FCK(cudaMalloc(&f.t8, sizeof(cplx) * 128));
+    FCK(cudaMalloc(&f.t9, sizeof(cplx) * 256));
     FCK(cudaMalloc(&f.emono, sizeof(cplx) * 4096));
-    FCK(cudaMemcpy(f.tw, tw.data(), sizeof(cplx) * 1024, cudaMemcpyHostToDevice));
-    FCK(cudaMemcpy(f.tw9e, tw9e.data(), sizeof(cplx) * 256, cudaMemcpyHostToDevice));
+    FCK(cudaMemcpy(f.t2, t2.data(), sizeof(cplx) * 128, cudaMemcpyHostToDevice));
+    FCK(cudaMemcpy(f.t8, t8.data(), sizeof(cplx) * 128, cudaMemcpyHostToDevice));
+    FCK(cudaMemcpy(f.t9, t9.data(), sizeof(cplx) * 256, cudaMemcpyHostToDevice));
     FCK(cudaMemcpy(f.emono, emono.data(), sizeof(cplx) * 4096, cudaMemcpyHostToDevice));
     FCK(cudaMemcpyToSymbol(c_tw1, tw1.data(), sizeof(cplx) * 16));
     FCK(cudaMemcpyToSymbol(c_e16, e16.data(), sizeof(cplx) * 16));
@@ -428,7 +446,7 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
 static inline int fast_launch(FastKeys &f, const mktfhe_params &p, fast::Args a, cudaStream_t stream, int *launches, std::string &err) {
     using namespace fast;
     if (!f.built) { err = "FAST keys not built"; return -3; }
-    a.brk = f.d_brk; a.tb = Tables{f.tw, f.tw9e, f.emono};
+    a.brk = f.d_brk; a.tb = Tables{f.t2, f.t8, f.t9, f.emono};
     a.n = p.n; a.k = p.k; a.l = p.l_gsw; a.logB = p.logB_gsw; a.l_lev = p.l_lev; a.logB_lev = p.logB_lev;
     a.R = 1 + (p.k - 1) * p.l_lev; a.lwe_words = (int)mktfhe_lwe_words(&p);
     const unsigned grid = (unsigned)((a.units + U - 1) / U);
