@@ -155,8 +155,8 @@ def cpu_baseline(ks, c1, c2, budget_s: float = 12.0, max_threads: int = 0) -> di
     p = ks.params
     orc = O.Oracle(p, ks.brk, ks.ksk, ks.rlk if p.scheme in (P.KMS, P.KMS_BLOCK) else None,
                    ks.pubb if p.is_mk else None, ks.crs_fft)
-    threads = O.max_threads() if max_threads <= 0 else max_threads
-    threads = max(1, min(threads, os.cpu_count() or 1))
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the num_threads clause overrides it)
+    threads = len(os.sched_getaffinity(0)) if max_threads <= 0 else max_threads
     n0 = min(threads, c1.shape[0])
     t = time.perf_counter()
     orc.gate_batch(0, c1[:n0], c2[:n0], threads)
@@ -201,13 +201,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        ks = KeySet(p, seed=KEY_SEED)
-        nsample = min(batch, max(8, 4 * (os.cpu_count() or 1)))
+        ks = KeySet(p, seed=KEY_SEED, nthreads=len(os.sched_getaffinity(0)))
+        nsample = min(batch, 2048)
         _, _, c1, c2 = make_inputs(ks, nsample, 0)
         vals = []
         info = None
         for it in range(args.warmup + args.steps):
-            info, _, n = cpu_baseline(ks, c1, c2, budget_s=6.0)
+            info, _, n = cpu_baseline(ks, c1, c2, budget_s=8.0)
             if it >= args.warmup:
                 vals.append(info["value"])
         v = float(np.mean(vals)) if vals else info["value"]

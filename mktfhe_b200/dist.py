@@ -64,7 +64,8 @@ def setup_replicated(p: Params, seed: int, device_index: int, rank: int, world: 
     """Key generation on rank 0, NCCL broadcast, upload from device memory on every rank.
     Returns (Scheme, KeySet); ranks other than 0 hold secret keys only (for encrypting / checking their shard)."""
     from .scheme import Scheme
-    ks = KeySet(p, seed=seed, secret_only=(rank != 0))
+    import os
+    ks = KeySet(p, seed=seed, secret_only=(rank != 0), nthreads=max(1, len(os.sched_getaffinity(0)) // max(1, min(world, 8))) if rank else len(os.sched_getaffinity(0)))
     s = Scheme(p, device_index)
     if world == 1:
         for i, q in enumerate(ks.parties):
