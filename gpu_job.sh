@@ -1,6 +1,10 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-nvidia-smi -L
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 1500 gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 2>&1 | tail -3
+python -m pytest tests/test_gpu_scale.py -m gpu -x -q -s 2>&1 | tail -12
+python bench.py --workload kms8 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_kms8.json 2> gpurun_out/bench_kms8.err; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_kms8.json'))
+print(d['value'], d['e2e']['value'], d['stage_ms_last_step'], d['roofline']['frac'], d['decrypt_check'], d['keygen_and_upload_s'])
+PY
+tail -3 gpurun_out/bench_kms8.err

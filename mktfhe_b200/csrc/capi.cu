@@ -142,7 +142,7 @@ int run_prep(mktfhe_ctx *ctx, int op, const uint32_t *in1, const uint32_t *in2, 
 }
 
 int run_phase1(mktfhe_ctx *ctx, const uint32_t *tilde, cplx *lev, size_t gates) {
-    if (ctx->mode == MKTFHE_MODE_FAST) return fast_phase1(ctx->fast, ctx->p, tilde, lev, gates, ctx->stream, &ctx->launches, ctx->err);
+    if (ctx->mode == MKTFHE_MODE_FAST && fast_supported(ctx->p)) return fast_phase1(ctx->fast, ctx->p, tilde, lev, gates, ctx->stream, &ctx->launches, ctx->err);
     RgswArgs a{};
     a.tilde = tilde; a.lev_out = lev; a.mode = RG_MODE_KMS;
     return run_rgsw(ctx, a, gates * ctx->R);
@@ -179,14 +179,30 @@ int run_ccs(mktfhe_ctx *ctx, const uint32_t *tilde, uint32_t *acc, size_t gates)
     return 0;
 }
 
+constexpr int KS_TILE = 16;
+
 int run_keyswitch(mktfhe_ctx *ctx, const void *acc, uint32_t *out, size_t gates) {
     const mktfhe_params &p = ctx->p;
     KsArgs a{};
     a.acc = acc; a.ksk = ctx->d_ksk; a.out = out;
     a.N = ctx->N; a.n = p.n; a.k = p.k; a.f = p.f; a.logD = p.logD; a.Dk = mktfhe_ksk_rows(&p);
     a.bits64 = ctx->bits == 64; a.block = ctx->block;
-    const size_t smem = keyswitch_smem_bytes(ctx->N, p.f, p.n);
-    k_keyswitch<<<(unsigned)gates, MK_THREADS, smem, ctx->stream>>>(a);
+    if (ctx->mode == MKTFHE_MODE_STRICT || p.f * p.logD != 16 || p.logD != 2) {
+        // reference loop order: one gate per CTA, parties in sequence
+        const size_t smem = keyswitch_smem_bytes(ctx->N, p.f, p.n);
+        k_keyswitch<<<(unsigned)gates, MK_THREADS, smem, ctx->stream>>>(a);
+    } else {
+        CK(cudaMemsetAsync(out, 0, gates * mktfhe_lwe_words(&p) * 4, ctx->stream));
+        const size_t smem = (size_t)ctx->N * KS_TILE * sizeof(uint16_t);
+        const dim3 grid((unsigned)((gates + KS_TILE - 1) / KS_TILE), (unsigned)p.k);
+        if (ctx->block) {
+            CK(cudaFuncSetAttribute(k_keyswitch_tiled<true, KS_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_keyswitch_tiled<true, KS_TILE><<<grid, MK_THREADS, smem, ctx->stream>>>(a, (int)gates);
+        } else {
+            CK(cudaFuncSetAttribute(k_keyswitch_tiled<false, KS_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_keyswitch_tiled<false, KS_TILE><<<grid, MK_THREADS, smem, ctx->stream>>>(a, (int)gates);
+        }
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -376,7 +392,6 @@ void mktfhe_ctx_destroy(mktfhe_ctx *ctx) {
 int mktfhe_set_mode(mktfhe_ctx *ctx, int mode) {
     if (!ctx) return MKTFHE_ERR_ARG;
     if (mode != MKTFHE_MODE_STRICT && mode != MKTFHE_MODE_FAST) return fail(ctx, MKTFHE_ERR_ARG, "bad mode");
-    if (mode == MKTFHE_MODE_FAST && !fast_supported(ctx->p)) return fail(ctx, MKTFHE_ERR_PARAMS, "FAST mode covers KMS / KMS_BLOCK phase 1; this scheme runs STRICT");
     ctx->mode = mode;
     return 0;
 }
@@ -437,10 +452,8 @@ int mktfhe_finalize_keys(mktfhe_ctx *ctx) {
         k_build_monomials<512><<<(2 * ctx->N + G - 1) / G, MK_THREADS, smem, ctx->stream>>>(ctx->mono, ctx->tables());
     }
     CK(cudaGetLastError());
-    if (fast_supported(ctx->p)) {
-        if ((rc = fast_build(ctx->fast, ctx->p, ctx->brk, ctx->stream, ctx->err))) return rc;
-        ctx->mode = MKTFHE_MODE_FAST;
-    }
+    if (fast_supported(ctx->p) && (rc = fast_build(ctx->fast, ctx->p, ctx->brk, ctx->stream, ctx->err))) return rc;
+    ctx->mode = MKTFHE_MODE_FAST;          // production default; floating-point stages without a FAST kernel run the STRICT one
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->finalized = true;
     return 0;

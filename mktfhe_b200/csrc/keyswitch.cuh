@@ -106,3 +106,114 @@ __global__ void __launch_bounds__(MK_THREADS) k_keyswitch(const KsArgs a) {
 }
 
 static inline size_t keyswitch_smem_bytes(int N, int f, int n) { return (size_t)N * f + (size_t)n * 4 + 16; }
+
+// ---------------------------------------------------------------------------------------------------
+// Tiled key switch (production): one CTA = G gates x one party.  All G gates walk (c, level) together, so
+// each selected ksk row is fetched from L2 once per tile and served to the other gates from L1; the digits
+// of the tile are staged in shared memory as 2-bit fields (f*logD = 16 bits per coefficient).
+// Integer adds commute, so the per-party partial sums of b are combined with atomicAdd into a zeroed output.
+template <bool BLOCK, int G>
+__global__ void __launch_bounds__(MK_THREADS) k_keyswitch_tiled(const KsArgs a, int batch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t *dig = reinterpret_cast<uint16_t *>(smem_raw);             // [N][G]
+    const int tid = threadIdx.x, p = blockIdx.y, g0 = blockIdx.x * G;
+    const int N = a.N, n = a.n, f = a.f, row = n + 1;
+    constexpr int MAXC = 3;
+    const int ng = min(G, batch - g0);
+    auto A = [&](int g, int comp, int c) -> uint32_t {
+        const size_t off = ((size_t)(g0 + g) * (a.k + 1) + comp) * N + c;
+        return a.bits64 ? (uint32_t)(reinterpret_cast<const uint64_t *>(a.acc)[off] >> 32)
+                        : reinterpret_cast<const uint32_t *>(a.acc)[off];
+    };
+    auto extract = [&](int g, int c) -> uint32_t { return c == 0 ? A(g, 1 + p, 0) : 0u - A(g, 1 + p, N - c); };
+
+    // stage digits: field lv (0 = most significant) of coefficient c sits at bits [2*(f-1-lv), +2)
+    for (int i = tid; i < N * G; i += MK_THREADS) {
+        const int c = i / G, g = i % G;
+        uint16_t packed = 0;
+        if (g < ng && !(BLOCK && c < n)) {
+            uint32_t ai = divbits<uint32_t>(extract(g, c), 32 - f * a.logD);
+            if (!BLOCK) packed = (uint16_t)ai;                          // unbalanced digits are the bit fields themselves
+            else {                                                      // balanced: gsw.jl:42-52, two's-complement 2-bit fields
+                uint32_t acc_bits = 0;
+                for (int lv = f - 1; lv >= 1; lv--) {
+                    const uint32_t d = ai & 3u;
+                    ai >>= 2; ai += d >> 1;
+                    acc_bits |= d << (2 * (f - 1 - lv));
+                }
+                acc_bits |= (ai & 3u) << (2 * (f - 1));
+                packed = (uint16_t)acc_bits;
+            }
+        }
+        dig[c * G + g] = packed;
+    }
+    __syncthreads();
+
+    uint32_t sum[G][MAXC];
+#pragma unroll
+    for (int g = 0; g < G; g++)
+#pragma unroll
+        for (int q = 0; q < MAXC; q++) sum[g][q] = 0u;
+    const uint32_t *ksk = a.ksk[p];
+    const size_t lvl_stride = row, dig_stride = (size_t)f * row;
+    const bool has[MAXC] = {tid < row, tid + MK_THREADS < row, tid + 2 * MK_THREADS < row};
+
+    // Per (c, level): fetch the Dk candidate rows first (independent coalesced loads, one L2 latency, pipelined across
+    // iterations), then let every gate of the tile pick its row with a warp-uniform branch: no memory operation sits
+    // on the gates' dependency chain.
+    constexpr int DK = BLOCK ? 2 : 3;
+    for (int c = BLOCK ? n : 0; c < N; c++) {
+        const uint32_t *base = ksk + (size_t)c * DK * dig_stride + tid;
+        uint32_t w[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) w[g] = dig[c * G + g];
+#pragma unroll 4
+        for (int lv = 0; lv < f; lv++) {
+            const int sh = 2 * (f - 1 - lv);
+            const uint32_t *lbase = base + lv * lvl_stride;
+            uint32_t x[DK][MAXC];
+#pragma unroll
+            for (int v = 0; v < DK; v++)
+#pragma unroll
+                for (int q = 0; q < MAXC; q++) x[v][q] = has[q] ? __ldg(lbase + (size_t)v * dig_stride + q * MK_THREADS) : 0u;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const uint32_t d = (w[g] >> sh) & 3u;                   // uniform over the CTA
+                if (!BLOCK) {
+                    if (d == 1) {
+#pragma unroll
+                        for (int q = 0; q < MAXC; q++) sum[g][q] += x[0][q];
+                    } else if (d == 2) {
+#pragma unroll
+                        for (int q = 0; q < MAXC; q++) sum[g][q] += x[1][q];
+                    } else if (d == 3) {
+#pragma unroll
+                        for (int q = 0; q < MAXC; q++) sum[g][q] += x[2][q];
+                    }
+                } else {                                                // d = 1: +row 1; d = 3 (-1): -row 1; d = 2 (-2): -row 2
+                    if (d == 1) {
+#pragma unroll
+                        for (int q = 0; q < MAXC; q++) sum[g][q] += x[0][q];
+                    } else if (d == 3) {
+#pragma unroll
+                        for (int q = 0; q < MAXC; q++) sum[g][q] -= x[0][q];
+                    } else if (d == 2) {
+#pragma unroll
+                        for (int q = 0; q < MAXC; q++) sum[g][q] -= x[1][q];
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        if (g >= ng) break;
+        uint32_t *out = a.out + (size_t)(g0 + g) * (1 + (size_t)n * a.k);
+#pragma unroll
+        for (int q = 0; q < MAXC; q++) {
+            const int col = tid + q * MK_THREADS;
+            if (col == 0) atomicAdd(out, sum[g][q] + (p == 0 ? A(g, 0, 0) : 0u));      // res.b = acc.b[0] + sum of parts
+            else if (col < row) out[1 + (size_t)p * n + (col - 1)] = sum[g][q] + ((BLOCK && col - 1 < n) ? extract(g, col - 1) : 0u);
+        }
+    }
+}
