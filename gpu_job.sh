@@ -1,10 +1,14 @@
-set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_scale.py -m gpu -x -q -s 2>&1 | tail -12
-python bench.py --workload kms8 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_kms8.json 2> gpurun_out/bench_kms8.err; python - <<'PY'
+timeout 600 python -m pytest tests/test_gpu_fast.py -m gpu -x -q -s 2>&1 | tail -12
+for w in kms2 kms8block; do
+  timeout 600 python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
+  python - <<PY
 import json
-d=json.load(open('gpurun_out/bench_kms8.json'))
-print(d['value'], d['e2e']['value'], d['stage_ms_last_step'], d['roofline']['frac'], d['decrypt_check'], d['keygen_and_upload_s'])
+try:
+    d=json.load(open('gpurun_out/bench_$w.json'))
+    print('$w', round(d['value'],1), d['mode'], {k:round(v,2) for k,v in d['stage_ms_last_step'].items()}, 'frac', round(d['roofline']['frac'],3), d['decrypt_check'])
+except Exception as e:
+    print('$w FAILED', e); print(open('gpurun_out/bench_$w.err').read()[-1500:])
 PY
-tail -3 gpurun_out/bench_kms8.err
+done

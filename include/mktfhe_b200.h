@@ -117,6 +117,10 @@ int mktfhe_keyswitch_batch(mktfhe_ctx *ctx, const void *acc, uint32_t *lwe_out, 
  * (bootstrapping.jl:47-74, 413-438). */
 int mktfhe_cmux_step_batch(mktfhe_ctx *ctx, int party, int idx, const uint32_t *atilde, void *acc_rows,
                            size_t batch);
+/* One block iteration of the LMSS / KMS_BLOCK loop (bootstrapping.jl:124-163, 624-655) on `batch` independent rows:
+ * atilde[g][ell] are the rotations of block `blk`'s key bits. */
+int mktfhe_block_step_batch(mktfhe_ctx *ctx, int party, int blk, const uint32_t *atilde, void *acc_rows,
+                            size_t batch);
 /* fftto! / ifftto! (fft.jl:57-63,74-81) and poly decompto! (gsw.jl:86-96) on `batch` polynomials.
  * bits = 32 / 64 selects the torus; spectra in the reference's slot order; STRICT arithmetic. */
 int mktfhe_fft_batch(mktfhe_ctx *ctx, int bits, const void *polys, double *spectra, size_t batch);

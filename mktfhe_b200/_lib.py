@@ -15,7 +15,7 @@ EXPORTS = [
     "mktfhe_upload_party_key", "mktfhe_upload_common", "mktfhe_finalize_keys",
     "mktfhe_gate_batch", "mktfhe_bootstrap_batch", "mktfhe_gate_batch_dev", "mktfhe_sync", "mktfhe_stream",
     "mktfhe_gate_linear_batch", "mktfhe_modswitch_batch", "mktfhe_blindrotate_batch", "mktfhe_phase1_batch",
-    "mktfhe_keyswitch_batch", "mktfhe_cmux_step_batch", "mktfhe_fft_batch", "mktfhe_ifft_batch",
+    "mktfhe_keyswitch_batch", "mktfhe_cmux_step_batch", "mktfhe_block_step_batch", "mktfhe_fft_batch", "mktfhe_ifft_batch",
     "mktfhe_decomp_batch", "mktfhe_last_stage_ms", "mktfhe_measure_dfma_peak",
 ]
 
@@ -52,6 +52,7 @@ def lib() -> ctypes.CDLL:
     L.mktfhe_phase1_batch.argtypes = [vp, vp, vp, sz]
     L.mktfhe_keyswitch_batch.argtypes = [vp, vp, vp, sz]
     L.mktfhe_cmux_step_batch.argtypes = [vp, i32, i32, vp, vp, sz]
+    L.mktfhe_block_step_batch.argtypes = [vp, i32, i32, vp, vp, sz]
     L.mktfhe_fft_batch.argtypes = [vp, i32, vp, vp, sz]
     L.mktfhe_ifft_batch.argtypes = [vp, i32, vp, vp, sz]
     L.mktfhe_decomp_batch.argtypes = [vp, i32, i32, i32, vp, vp, sz]

@@ -127,7 +127,7 @@ int run_rgsw(mktfhe_ctx *ctx, RgswArgs a, size_t units) {
     a.brk = ctx->d_brk; a.mono = ctx->mono; a.tb = ctx->tables();
     a.n = p.n; a.d = p.d; a.k = p.k; a.l = p.l_gsw; a.logB = p.logB_gsw;
     a.l_lev = p.l_lev; a.logB_lev = p.logB_lev; a.R = ctx->R; a.lwe_words = (int)mktfhe_lwe_words(&p);
-    const bool blk = ctx->block && a.mode != RG_MODE_STEP;
+    const bool blk = ctx->block && (a.mode != RG_MODE_STEP || a.step_block);
     if (ctx->bits == 64) return blk ? launch_rgsw<uint64_t, 1024, 3>(ctx, a, units) : launch_rgsw<uint64_t, 1024, 1>(ctx, a, units);
     return blk ? launch_rgsw<uint32_t, 512, 3>(ctx, a, units) : launch_rgsw<uint32_t, 512, 1>(ctx, a, units);
 }
@@ -611,22 +611,24 @@ int mktfhe_keyswitch_batch(mktfhe_ctx *ctx, const void *acc, uint32_t *lwe_out, 
     return 0;
 }
 
-int mktfhe_cmux_step_batch(mktfhe_ctx *ctx, int party, int idx, const uint32_t *atilde, void *acc_rows, size_t batch) {
+static int step_impl(mktfhe_ctx *ctx, int party, int idx, const uint32_t *atilde, void *acc_rows, size_t batch, bool block_step) {
     int rc;
     if ((rc = check_ready(ctx))) return rc;
     if (ctx->p.scheme == MKTFHE_CCS) return fail(ctx, MKTFHE_ERR_PARAMS, "CCS has no RGSW step");
-    if (party < 0 || party >= ctx->nparties || idx < 0 || idx >= ctx->p.n || !atilde || !acc_rows) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
+    if (block_step && !ctx->block) return fail(ctx, MKTFHE_ERR_PARAMS, "block step needs LMSS / KMS_BLOCK");
+    const int lim = block_step ? ctx->p.d : ctx->p.n, per = block_step ? ctx->p.ell : 1;
+    if (party < 0 || party >= ctx->nparties || idx < 0 || idx >= lim || !atilde || !acc_rows) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
     const size_t row_bytes = (size_t)2 * ctx->N * (ctx->bits / 8);
     uint32_t *d_at = nullptr; void *d_rows = nullptr;
-    CK(cudaMalloc(&d_at, batch * 4));
+    CK(cudaMalloc(&d_at, batch * 4 * per));
     CK(cudaMalloc(&d_rows, batch * row_bytes));
-    CK(cudaMemcpyAsync(d_at, atilde, batch * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_at, atilde, batch * 4 * per, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_rows, acc_rows, batch * row_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (ctx->mode == MKTFHE_MODE_FAST && fast_supported(ctx->p)) {
+    if (ctx->mode == MKTFHE_MODE_FAST && fast_supported(ctx->p) && (block_step == ctx->block)) {
         rc = fast_cmux_step(ctx->fast, ctx->p, party, idx, d_at, d_rows, batch, ctx->stream, &ctx->launches, ctx->err);
     } else {
         RgswArgs a{};
-        a.tilde = d_at; a.acc_io = d_rows; a.mode = RG_MODE_STEP; a.step_party = party; a.step_idx = idx;
+        a.tilde = d_at; a.acc_io = d_rows; a.mode = RG_MODE_STEP; a.step_party = party; a.step_idx = idx; a.step_block = block_step;
         rc = run_rgsw(ctx, a, batch);
     }
     if (!rc) {
@@ -635,6 +637,14 @@ int mktfhe_cmux_step_batch(mktfhe_ctx *ctx, int party, int idx, const uint32_t *
     }
     cudaFree(d_at); cudaFree(d_rows);
     return rc;
+}
+
+int mktfhe_cmux_step_batch(mktfhe_ctx *ctx, int party, int idx, const uint32_t *atilde, void *acc_rows, size_t batch) {
+    return step_impl(ctx, party, idx, atilde, acc_rows, batch, false);
+}
+
+int mktfhe_block_step_batch(mktfhe_ctx *ctx, int party, int blk, const uint32_t *atilde, void *acc_rows, size_t batch) {
+    return step_impl(ctx, party, blk, atilde, acc_rows, batch, true);
 }
 
 int mktfhe_fft_batch(mktfhe_ctx *ctx, int bits, const void *polys, double *spectra, size_t batch) {

@@ -20,6 +20,7 @@
 //   * (X^a - 1)/H is rebuilt per slot from two small tables: exp(-i*pi*(4*brv6(t)+1)*a/N) (per thread) times a
 //     16th root of unity (per register slot); the 1/H of the inverse transform rides on it.
 #pragma once
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "common.cuh"
@@ -222,13 +223,14 @@ struct Args {
     cplx *lev_out;                // [B][R][2][H], reference slot order
     uint64_t *acc_io;             // step mode: [units][2][N]
     int step_mode, step_party, step_idx;
-    int n, k, l, logB, l_lev, logB_lev, R, lwe_words;
+    int n, d, k, l, logB, l_lev, logB_lev, R, lwe_words;
     size_t units;
 };
 
 constexpr size_t SMEM_UNIT = (size_t)2 * N * 8 + (size_t)XB_LEN * 16;         // acc b, a + exchange buffer
 constexpr size_t SMEM_BYTES = U * SMEM_UNIT + (size_t)(128 + 128 + 256) * 16;  // + t2, t8, t9
 
+template <int ELL>
 __global__ void __launch_bounds__(CTA, 1) k_phase1(const Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, unit_l = tid / UT, t = tid % UT;
@@ -271,15 +273,25 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1(const Args a) {
     const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));       // 2^52 + B/2
     const cplx *brk = a.brk[party];
     const size_t per_idx = (size_t)4 * l * H;
-    const uint32_t *at_src = a.step_mode ? a.tilde + unit : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
-    const int nsteps = a.step_mode ? 1 : a.n;
+    const uint32_t *at_src = a.step_mode ? a.tilde + unit * ELL : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
+    const int nsteps = a.step_mode ? 1 : (ELL == 1 ? a.n : a.d);
     int brv6t = (int)(__brev((unsigned)t) >> 26);
 
     for (int step = 0; step < nsteps; step++) {
-        const uint32_t at = at_src[a.step_mode ? 0 : step];
-        if (at == 0) continue;                                                        // :413
-        const int idx = a.step_mode ? a.step_idx : step;
+        // ELL == 1: one LWE index per step (:412-438).  ELL > 1: one block of ELL key bits per step (:624-655);
+        // the block's monomials are folded into the keys so one accumulator pair serves the whole block:
+        //   sum_bit mono_bit * (sum_dg D_dg * K_bit,dg)  =  sum_dg D_dg * (sum_bit mono_bit * K_bit,dg)
+        uint32_t atv[ELL];
+        bool any = false;
+#pragma unroll
+        for (int b = 0; b < ELL; b++) { atv[b] = at_src[(a.step_mode ? 0 : step * ELL) + b]; any |= atv[b] > 0; }
+        if (!any) continue;                                                           // :413 / whole-block no-op
+        const uint32_t at = atv[0];
+        const int idx = (a.step_mode ? a.step_idx : step) * ELL;
         const cplx *kidx = brk + (size_t)idx * per_idx + t;
+        cplx m1v[ELL];
+#pragma unroll
+        for (int b = 0; b < ELL; b++) m1v[b] = __ldg(&a.tb.emono[((4 * brv6t + 1) * atv[b]) & 4095]);
 
         cplx tb_[16], ta_[16];
 #pragma unroll
@@ -298,22 +310,42 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1(const Args a) {
             }
             fft_fwd(x, xb, tw2, tw8, tw9e, t, unit_l);
             const cplx *kb = kidx + (size_t)(dg * 2) * H, *ka = kb + H;
+            if (ELL == 1) {
 #pragma unroll
-            for (int e = 0; e < 16; e++) {
-                const cplx wb = __ldg(kb + e * UT), wa = __ldg(ka + e * UT);
-                tb_[e] = cmac_f(tb_[e], x[e], wb);
-                ta_[e] = cmac_f(ta_[e], x[e], wa);
+                for (int e = 0; e < 16; e++) {
+                    const cplx wb = __ldg(kb + e * UT), wa = __ldg(ka + e * UT);
+                    tb_[e] = cmac_f(tb_[e], x[e], wb);
+                    ta_[e] = cmac_f(ta_[e], x[e], wa);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
+                    cplx kcb = make_double2(0.0, 0.0), kca = kcb;
+#pragma unroll
+                    for (int b = 0; b < ELL; b++) {
+                        if (atv[b] == 0) continue;
+                        cplx mo = cmul_f(m1v[b], c_e16[(atv[b] * b4) & 15]);
+                        mo.x -= 1.0 / H;
+                        kcb = cmac_f(kcb, mo, __ldg(kb + b * per_idx + e * UT));
+                        kca = cmac_f(kca, mo, __ldg(ka + b * per_idx + e * UT));
+                    }
+                    tb_[e] = cmac_f(tb_[e], x[e], kcb);
+                    ta_[e] = cmac_f(ta_[e], x[e], kca);
+                }
             }
         }
         // (X^a - 1) / H per slot: slot n = 16t + e evaluates at exp(-i*pi*(4*brv10(n)+1)/N), brv10(n) = 64*brv4(e) + brv6(t)
-        const cplx m1 = __ldg(&a.tb.emono[((4 * brv6t + 1) * at) & 4095]);
+        if (ELL == 1) {
+            const cplx m1 = m1v[0];
 #pragma unroll
-        for (int e = 0; e < 16; e++) {
-            const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
-            cplx mo = cmul_f(m1, c_e16[(at * b4) & 15]);
-            mo.x -= 1.0 / H;
-            tb_[e] = cmul_f(mo, tb_[e]);
-            ta_[e] = cmul_f(mo, ta_[e]);
+            for (int e = 0; e < 16; e++) {
+                const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
+                cplx mo = cmul_f(m1, c_e16[(at * b4) & 15]);
+                mo.x -= 1.0 / H;
+                tb_[e] = cmul_f(mo, tb_[e]);
+                ta_[e] = cmul_f(mo, ta_[e]);
+            }
         }
         fft_inv(tb_, xb, tw2, tw8, tw9e, t, unit_l);
 #pragma unroll
@@ -350,6 +382,339 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1(const Args a) {
     }
 }
 
+// ======================================================================================================
+// TMEM variant (default).  Blackwell's tensor memory is lane-private per warp quadrant, which is exactly the
+// ownership pattern of this kernel: thread t only ever touches RLWE-accumulator coefficients t + 64m (+H) and
+// RGSW-accumulator slots 16t + e.  Both accumulators therefore live in TMEM (tcgen05.ld / tcgen05.st,
+// measured ~850 B/clk/SM against 128 B/clk/SM for shared memory):
+//   per thread 256 columns: [0,64) acc.b  [64,128) acc.a  [128,192) tacc.b  [192,256) tacc.a
+//   warp w -> lanes 32*(w%4).., columns 256*(w/4)..   (8 warps fill the 512-column allocation of the CTA)
+// That frees 128 registers per thread (bootstrapping-key values are prefetched before the pass that precedes
+// their use) and 128 KiB of shared memory (the exchange buffer is double-buffered: 2 barriers per transform).
+__device__ __forceinline__ void tm_st16(uint32_t addr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tm_ld16(uint32_t addr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 4 complex doubles <-> 16 TMEM columns
+__device__ __forceinline__ void tm_ld_c4(uint32_t addr, cplx (&z)[4]) {
+    uint32_t v[16];
+    tm_ld16(addr, v);
+    tm_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 4; i++) z[i] = make_double2(__hiloint2double((int)v[4 * i + 1], (int)v[4 * i]), __hiloint2double((int)v[4 * i + 3], (int)v[4 * i + 2]));
+}
+__device__ __forceinline__ void tm_st_c4(uint32_t addr, const cplx (&z)[4]) {
+    uint32_t v[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        v[4 * i] = (uint32_t)__double2loint(z[i].x); v[4 * i + 1] = (uint32_t)__double2hiint(z[i].x);
+        v[4 * i + 2] = (uint32_t)__double2loint(z[i].y); v[4 * i + 3] = (uint32_t)__double2hiint(z[i].y);
+    }
+    tm_st16(addr, v);
+}
+
+constexpr int TM_ACC_B = 0, TM_ACC_A = 64, TM_TACC_B = 128, TM_TACC_A = 192;
+constexpr size_t SMEM_UNIT_TM = (size_t)2 * XB_LEN * 16;                                   // two exchange buffers
+constexpr size_t SMEM_BYTES_TM = U * SMEM_UNIT_TM + (size_t)(128 + 128 + 256) * 16 + 16;
+
+// forward transform with double-buffered exchanges; `mid1` / `mid2` run after the exchange reads, i.e. while the
+// pass that follows is still ahead: the caller issues its key prefetches there.
+template <class F1, class F2>
+__device__ __forceinline__ void fft_fwd2(cplx (&x)[16], cplx *xa, cplx *xc, const cplx *tw2, const cplx *tw8, const cplx *tw9e,
+                                         int t, int unit, F1 mid1, F2 mid2) {
+    pass1_fwd(x);
+#pragma unroll
+    for (int m = 0; m < 16; m++) xa[t + 68 * m] = x[m];
+    unit_bar(unit);
+    const int blk = t >> 2, o = t & 3;
+#pragma unroll
+    for (int q = 0; q < 16; q++) x[q] = xa[68 * blk + o + 4 * q];
+    mid1();
+    pass2_fwd(x, tw2, blk);
+#pragma unroll
+    for (int q = 0; q < 16; q++) xc[68 * blk + o + 4 * q + (q >> 2)] = x[q];
+    unit_bar(unit);
+#pragma unroll
+    for (int e = 0; e < 16; e++) x[e] = xc[17 * t + e];
+    mid2();
+    pass3_fwd(x, tw8, tw9e, t);
+}
+// The two buffers strictly alternate over the whole kernel (forward: xa then xc; inverse: xa then xc as well), so a
+// buffer is only rewritten after a barrier that every reader of its previous contents has passed.
+__device__ __forceinline__ void fft_inv2(cplx (&x)[16], cplx *xa, cplx *xc, const cplx *tw2, const cplx *tw8, const cplx *tw9e, int t, int unit) {
+    pass3_inv(x, tw8, tw9e, t);
+#pragma unroll
+    for (int e = 0; e < 16; e++) xa[17 * t + e] = x[e];
+    unit_bar(unit);
+    const int blk = t >> 2, o = t & 3;
+#pragma unroll
+    for (int q = 0; q < 16; q++) x[q] = xa[68 * blk + o + 4 * q + (q >> 2)];
+    pass2_inv(x, tw2, blk);
+#pragma unroll
+    for (int q = 0; q < 16; q++) xc[68 * blk + o + 4 * q] = x[q];
+    unit_bar(unit);
+#pragma unroll
+    for (int m = 0; m < 16; m++) x[m] = xc[t + 68 * m];
+    pass1_inv(x);
+}
+
+template <int ELL>
+__global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, unit_l = tid / UT, t = tid % UT;
+    cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + U * SMEM_UNIT_TM), *tw8 = tw2 + 128, *tw9e = tw8 + 128;
+    uint32_t *tm_base_s = reinterpret_cast<uint32_t *>(tw9e + 256);
+    for (int i = tid; i < 256; i += CTA) { if (i < 128) { tw2[i] = a.tb.t2[i]; tw8[i] = a.tb.t8[i]; } tw9e[i] = a.tb.t9[i]; }
+    cplx *xa = reinterpret_cast<cplx *>(smem_raw + unit_l * SMEM_UNIT_TM), *xc = xa + XB_LEN;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"((uint32_t)__cvta_generic_to_shared(tm_base_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tm = *tm_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + 256u * (uint32_t)(warp >> 2);
+
+    const size_t unit = (size_t)blockIdx.x * U + unit_l;
+    if (unit < a.units) {
+        int gate, party, row = 0;
+        if (!a.step_mode) {
+            gate = (int)(unit / a.R);
+            const int r = (int)(unit % a.R);
+            party = r == 0 ? 0 : 1 + (r - 1) / a.l_lev;
+            row = r == 0 ? 0 : (r - 1) % a.l_lev;
+            uint32_t z[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) z[i] = 0u;
+            const uint64_t gv = t == 0 ? (uint64_t)1 << (64 - (row + 1) * a.logB_lev) : 0;   // bootstrapping.jl:402-408
+#pragma unroll
+            for (int c = 0; c < 128; c += 16) {                // tcgen05.st is warp-collective: same instruction on every lane
+                z[0] = c == 0 ? (uint32_t)gv : 0u;
+                z[1] = c == 0 ? (uint32_t)(gv >> 32) : 0u;
+                tm_st16(tm + c, z);
+            }
+        } else {
+            gate = (int)unit; party = a.step_party;
+            const uint64_t *src = a.acc_io + unit * 2 * N;
+#pragma unroll
+            for (int pz = 0; pz < 2; pz++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {                                             // 8 coefficients per 16 columns
+                    uint32_t v[16];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int ci = 8 * c + i;                                          // 0..31: m = ci & 15, upper half = ci >> 4
+                        const uint64_t w = src[pz * N + t + 64 * (ci & 15) + (ci >> 4) * H];
+                        v[2 * i] = (uint32_t)w; v[2 * i + 1] = (uint32_t)(w >> 32);
+                    }
+                    tm_st16(tm + pz * 64 + 16 * c, v);
+                }
+        }
+        tm_wait_st();
+
+        const int l = a.l, logB = a.logB;
+        const int bit = 64 - l * logB;
+        uint64_t cadd = (uint64_t)1 << (bit - 1);
+        for (int j = 0; j < l; j++) cadd += (uint64_t)1 << (bit + j * logB + logB - 1);
+        const uint32_t mask = (1u << logB) - 1;
+        const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));
+        const cplx *brk = a.brk[party];
+        const size_t per_idx = (size_t)4 * l * H;
+        const uint32_t *at_src = a.step_mode ? a.tilde + unit * ELL : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
+        const int nsteps = a.step_mode ? 1 : (ELL == 1 ? a.n : a.d);
+        const int brv6t = (int)(__brev((unsigned)t) >> 26);
+
+        for (int step = 0; step < nsteps; step++) {
+            uint32_t atv[ELL];
+            bool any = false;
+#pragma unroll
+            for (int b = 0; b < ELL; b++) { atv[b] = at_src[(a.step_mode ? 0 : step * ELL) + b]; any |= atv[b] > 0; }
+            if (!any) continue;
+            const int idx = (a.step_mode ? a.step_idx : step) * ELL;
+            const cplx *kidx = brk + (size_t)idx * per_idx + t;
+            cplx m1v[ELL];
+#pragma unroll
+            for (int b = 0; b < ELL; b++) m1v[b] = __ldg(&a.tb.emono[((4 * brv6t + 1) * atv[b]) & 4095]);
+
+            for (int dg = 0; dg < 2 * l; dg++) {
+                const uint32_t src = tm + (dg < l ? TM_ACC_B : TM_ACC_A);
+                const int sh = bit + (l - 1 - (dg < l ? dg : dg - l)) * logB;
+                cplx x[16];
+                {   // gadget digit of 32 coefficients -> 16 complex points (decomposition as in the shared-memory variant)
+                    uint32_t lo[32], hi[32];                   // coefficient m at columns 2m, 2m+1; m + 16 = upper half (n + H)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t v[16];
+                        tm_ld16(src + 16 * c, v);
+                        tm_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { lo[8 * c + i] = v[2 * i]; hi[8 * c + i] = v[2 * i + 1]; }
+                    }
+#pragma unroll
+                    for (int m = 0; m < 16; m++) {
+                        const uint64_t v0 = (((uint64_t)hi[m] << 32) | lo[m]) + cadd, v1 = (((uint64_t)hi[m + 16] << 32) | lo[m + 16]) + cadd;
+                        const uint32_t f0 = (uint32_t)(v0 >> sh) & mask, f1 = (uint32_t)(v1 >> sh) & mask;
+                        x[m] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
+                    }
+                }
+                const cplx *kb = kidx + (size_t)(dg * 2) * H, *ka = kb + H;
+                if (ELL == 1) {
+                    cplx wb[16], wa[16];
+                    fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l,
+                             [&]() {
+#pragma unroll
+                                 for (int e = 0; e < 16; e++) wb[e] = __ldg(kb + e * UT);
+                             },
+                             [&]() {
+#pragma unroll
+                                 for (int e = 0; e < 16; e++) wa[e] = __ldg(ka + e * UT);
+                             });
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        cplx zb[4], za[4];
+                        if (dg == 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) { zb[i] = cmul_f(x[4 * c + i], wb[4 * c + i]); za[i] = cmul_f(x[4 * c + i], wa[4 * c + i]); }
+                        } else {
+                            tm_ld_c4(tm + TM_TACC_B + 16 * c, zb);
+                            tm_ld_c4(tm + TM_TACC_A + 16 * c, za);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) { zb[i] = cmac_f(zb[i], x[4 * c + i], wb[4 * c + i]); za[i] = cmac_f(za[i], x[4 * c + i], wa[4 * c + i]); }
+                        }
+                        tm_st_c4(tm + TM_TACC_B + 16 * c, zb);
+                        tm_st_c4(tm + TM_TACC_A + 16 * c, za);
+                    }
+                } else {
+                    fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+                    // block: fold the monomials of the block's key bits into the keys (see k_phase1)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        cplx kv[ELL][2][4];
+#pragma unroll
+                        for (int b = 0; b < ELL; b++)
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                kv[b][0][i] = __ldg(kb + b * per_idx + (4 * c + i) * UT);
+                                kv[b][1][i] = __ldg(ka + b * per_idx + (4 * c + i) * UT);
+                            }
+                        cplx zb[4], za[4];
+                        if (dg != 0) { tm_ld_c4(tm + TM_TACC_B + 16 * c, zb); tm_ld_c4(tm + TM_TACC_A + 16 * c, za); }
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int e = 4 * c + i;
+                            const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
+                            cplx kcb = make_double2(0.0, 0.0), kca = kcb;
+#pragma unroll
+                            for (int b = 0; b < ELL; b++) {
+                                if (atv[b] == 0) continue;
+                                cplx mo = cmul_f(m1v[b], c_e16[(atv[b] * b4) & 15]);
+                                mo.x -= 1.0 / H;
+                                kcb = cmac_f(kcb, mo, kv[b][0][i]);
+                                kca = cmac_f(kca, mo, kv[b][1][i]);
+                            }
+                            if (dg == 0) { zb[i] = cmul_f(x[e], kcb); za[i] = cmul_f(x[e], kca); }
+                            else { zb[i] = cmac_f(zb[i], x[e], kcb); za[i] = cmac_f(za[i], x[e], kca); }
+                        }
+                        tm_st_c4(tm + TM_TACC_B + 16 * c, zb);
+                        tm_st_c4(tm + TM_TACC_A + 16 * c, za);
+                    }
+                }
+                tm_wait_st();
+            }
+            // both outputs: (x (X^a - 1)/H for ELL == 1) -> inverse transform -> round -> acc +=
+#pragma unroll 1
+            for (int pz = 0; pz < 2; pz++) {
+                cplx y[16];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    cplx z[4];
+                    tm_ld_c4(tm + (pz == 0 ? TM_TACC_B : TM_TACC_A) + 16 * c, z);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) y[4 * c + i] = z[i];
+                }
+                if (ELL == 1) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
+                        cplx mo = cmul_f(m1v[0], c_e16[(atv[0] * b4) & 15]);
+                        mo.x -= 1.0 / H;
+                        y[e] = cmul_f(mo, y[e]);
+                    }
+                }
+                fft_inv2(y, xa, xc, tw2, tw8, tw9e, t, unit_l);
+                const uint32_t dst = tm + (pz == 0 ? TM_ACC_B : TM_ACC_A);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {              // columns 16c..: coefficients 8c..8c+7 (m = ci & 15, upper half = ci >> 4)
+                    uint32_t v[16];
+                    tm_ld16(dst + 16 * c, v);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int ci = 8 * c + i, m = ci & 15;
+                        const uint64_t add = d2torus(ci < 16 ? y[m].x : -y[m].y);
+                        const uint64_t w = (((uint64_t)v[2 * i + 1] << 32) | v[2 * i]) + add;
+                        v[2 * i] = (uint32_t)w; v[2 * i + 1] = (uint32_t)(w >> 32);
+                    }
+                    tm_st16(dst + 16 * c, v);
+                }
+                tm_wait_st();
+            }
+        }
+
+        if (!a.step_mode) {            // fftto!(tacc, acc): bootstrapping.jl:441
+            cplx *out = a.lev_out + unit * 2 * H;
+#pragma unroll 1
+            for (int pz = 0; pz < 2; pz++) {
+                cplx x[16];
+                uint32_t lo[32], hi[32];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t v[16];
+                    tm_ld16(tm + pz * 64 + 16 * c, v);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { lo[8 * c + i] = v[2 * i]; hi[8 * c + i] = v[2 * i + 1]; }
+                }
+#pragma unroll
+                for (int m = 0; m < 16; m++) {
+                    const uint64_t v0 = ((uint64_t)hi[m] << 32) | lo[m], v1 = ((uint64_t)hi[m + 16] << 32) | lo[m + 16];
+                    x[m] = make_double2(__ll2double_rn((long long)v0), __ll2double_rn((long long)((uint64_t)0 - v1)));
+                }
+                fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+#pragma unroll
+                for (int e = 0; e < 16; e++) out[(size_t)pz * H + 16 * t + e] = x[e];
+            }
+        } else {
+            uint64_t *dst = a.acc_io + unit * 2 * N;
+#pragma unroll
+            for (int pz = 0; pz < 2; pz++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t v[16];
+                    tm_ld16(tm + pz * 64 + 16 * c, v);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int ci = 8 * c + i;
+                        dst[pz * N + t + 64 * (ci & 15) + (ci >> 4) * H] = ((uint64_t)v[2 * i + 1] << 32) | v[2 * i];
+                    }
+                }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tm_base_s));
+}
+
 // reference slot order [poly][16t + e] -> thread order [poly][e][t]
 __global__ void k_permute_brk(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,7 +733,9 @@ struct FastKeys {
     bool built = false;
 };
 
-static inline bool fast_supported(const mktfhe_params &p) { return p.scheme == MKTFHE_KMS && p.N == 2048; }
+static inline bool fast_supported(const mktfhe_params &p) {
+    return p.N == 2048 && (p.scheme == MKTFHE_KMS || (p.scheme == MKTFHE_KMS_BLOCK && p.ell == 3));
+}
 
 static inline void fast_free(FastKeys &f) {
     for (auto &q : f.brk) if (q) cudaFree(q);
@@ -438,7 +805,10 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
     }
     FCK(cudaMalloc(&f.d_brk, sizeof(cplx *) * f.brk.size()));
     FCK(cudaMemcpy(f.d_brk, f.brk.data(), sizeof(cplx *) * f.brk.size(), cudaMemcpyHostToDevice));
-    FCK(cudaFuncSetAttribute(k_phase1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    FCK(cudaFuncSetAttribute(k_phase1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    FCK(cudaFuncSetAttribute(k_phase1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    FCK(cudaFuncSetAttribute(k_phase1_tm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
+    FCK(cudaFuncSetAttribute(k_phase1_tm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
     f.built = true;
     return 0;
 }
@@ -450,7 +820,15 @@ static inline int fast_launch(FastKeys &f, const mktfhe_params &p, fast::Args a,
     a.n = p.n; a.k = p.k; a.l = p.l_gsw; a.logB = p.logB_gsw; a.l_lev = p.l_lev; a.logB_lev = p.logB_lev;
     a.R = 1 + (p.k - 1) * p.l_lev; a.lwe_words = (int)mktfhe_lwe_words(&p);
     const unsigned grid = (unsigned)((a.units + U - 1) / U);
-    k_phase1<<<grid, CTA, SMEM_BYTES, stream>>>(a);
+    a.d = p.d;
+    static const bool use_tmem = []() { const char *e = getenv("MKTFHE_FAST_KERNEL"); return !(e && std::string(e) == "smem"); }();
+    if (use_tmem) {
+        if (p.scheme == MKTFHE_KMS_BLOCK) k_phase1_tm<3><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
+        else k_phase1_tm<1><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
+    } else {
+        if (p.scheme == MKTFHE_KMS_BLOCK) k_phase1<3><<<grid, CTA, SMEM_BYTES, stream>>>(a);
+        else k_phase1<1><<<grid, CTA, SMEM_BYTES, stream>>>(a);
+    }
     if (launches) (*launches)++;
     FCK(cudaGetLastError());
     return 0;

@@ -14,7 +14,7 @@
 enum { RG_MODE_KMS = 0, RG_MODE_SK = 1, RG_MODE_STEP = 2 };
 
 struct RgswArgs {
-    const uint32_t *tilde;        // [B][1 + n*k]: b~, a~   (RG_MODE_STEP: [B] rotations)
+    const uint32_t *tilde;        // [B][1 + n*k]: b~, a~   (RG_MODE_STEP: [B][ELL] rotations)
     const cplx *const *brk;       // [k] party key pointers, reference slot order
     const cplx *mono;             // [2N][H] monomial table (scheme.jl:121-146)
     FftTables tb;
@@ -22,7 +22,7 @@ struct RgswArgs {
     void *acc_io;                 // RG_MODE_SK: out [B][2][N];  RG_MODE_STEP: in/out [B][2][N]
     int mode;
     int n, d, k, l, logB, l_lev, logB_lev, R, lwe_words;
-    int step_party, step_idx;
+    int step_party, step_idx, step_block;
 };
 
 // src/tfhe/bootstrapping.jl:11-22
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(MK_THREADS) k_rgsw_blindrotate(const RgswArgs 
     const cplx *brk = a.brk[party];
     const int l = a.l, nd = 2 * a.l;
     const size_t per_idx = (size_t)4 * l * H;
-    const uint32_t *at_src = a.mode == RG_MODE_STEP ? a.tilde + gate
+    const uint32_t *at_src = a.mode == RG_MODE_STEP ? a.tilde + (size_t)gate * ELL
                                                     : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
     const int nblk = a.mode == RG_MODE_STEP ? 1 : (ELL == 1 ? a.n : a.d);
 
@@ -76,9 +76,9 @@ __global__ void __launch_bounds__(MK_THREADS) k_rgsw_blindrotate(const RgswArgs 
         uint32_t at[ELL];
         bool any = false;
 #pragma unroll
-        for (int b = 0; b < ELL; b++) { at[b] = a.mode == RG_MODE_STEP ? at_src[0] : at_src[blk * ELL + b]; any |= at[b] > 0; }
+        for (int b = 0; b < ELL; b++) { at[b] = at_src[blk * ELL + b]; any |= at[b] > 0; }
         if (!any) continue;                                   // :48 / :413 ; block: whole-block no-op
-        const int idx0 = a.mode == RG_MODE_STEP ? a.step_idx : blk * ELL;
+        const int idx0 = (a.mode == RG_MODE_STEP ? a.step_idx : blk) * ELL;   // step mode: step_idx counts blocks when ELL > 1
 
         cplx tacc[ELL][2][SL];
 #pragma unroll

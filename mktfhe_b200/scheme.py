@@ -167,6 +167,13 @@ class Scheme:
         self._ck(_lib.lib().mktfhe_cmux_step_batch(self._h, party, idx, _ptr(at), _ptr(rows), rows.shape[0]), "cmux_step")
         return rows
 
+    def block_step(self, party, blk, atilde, acc_rows):
+        rows = np.array(acc_rows, dtype=self.torus_dtype, order="C", copy=True)
+        at = np.ascontiguousarray(atilde, dtype=np.uint32)
+        assert rows.ndim == 3 and at.shape == (rows.shape[0], self.params.ell)
+        self._ck(_lib.lib().mktfhe_block_step_batch(self._h, party, blk, _ptr(at), _ptr(rows), rows.shape[0]), "block_step")
+        return rows
+
     def fft(self, polys):
         polys = np.ascontiguousarray(polys)
         bits = polys.dtype.itemsize * 8

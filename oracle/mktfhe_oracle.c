@@ -381,6 +381,37 @@ void orc_cmux_step(const orc_ctx *c, int party, int idx, uint32_t atilde, void *
     free(tvec); free(tacc);
 }
 
+/* One block iteration (idx1) of the LMSS / KMS_block loop on one RLWE row: bootstrapping.jl:124-163 / :624-655.
+ * at: ell rotations of the block's key bits. */
+void orc_block_step(const orc_ctx *c, int party, int blk, const uint32_t *at, void *acc_row) {
+    const int N = c->p.N, H = c->F.H, l = c->p.l_gsw, logB = c->p.logB_gsw, ell = c->p.ell;
+    cplx *tvec = malloc(sizeof(cplx) * 2 * l * H), *t1 = malloc(sizeof(cplx) * 2 * H), *t2 = calloc(2 * H, sizeof(cplx));
+    if (c->bits == 32) {
+        uint32_t *acc = acc_row, *scr = malloc(sizeof(uint32_t) * (size_t)(l + 1) * N);
+        decomp_fft_row_32(tvec, acc, acc + N, l, logB, &c->F, scr);
+        for (int i2 = 0; i2 < ell; i2++) {
+            if (at[i2] == 0) continue;
+            rgsw_mac_32(t1, tvec, brk_rgsw(c, party, blk * ell + i2), l, H);
+            const cplx *mo = mono(c, at[i2]);
+            for (int s = 0; s < 2 * H; s++) t2[s] = cadd(t2[s], cmul(mo[s % H], t1[s]));
+        }
+        mono_ifft_add_32(acc, acc + N, t2, NULL, &c->F, scr + (size_t)l * N);
+        free(scr);
+    } else {
+        uint64_t *acc = acc_row, *scr = malloc(sizeof(uint64_t) * (size_t)(l + 1) * N);
+        decomp_fft_row_64(tvec, acc, acc + N, l, logB, &c->F, scr);
+        for (int i2 = 0; i2 < ell; i2++) {
+            if (at[i2] == 0) continue;
+            rgsw_mac_64(t1, tvec, brk_rgsw(c, party, blk * ell + i2), l, H);
+            const cplx *mo = mono(c, at[i2]);
+            for (int s = 0; s < 2 * H; s++) t2[s] = cadd(t2[s], cmul(mo[s % H], t1[s]));
+        }
+        mono_ifft_add_64(acc, acc + N, t2, NULL, &c->F, scr + (size_t)l * N);
+        free(scr);
+    }
+    free(tvec); free(t1); free(t2);
+}
+
 /* KMS: bootstrapping.jl:389-443 ; KMS_BLOCK: :599-659 */
 void orc_phase1(const orc_ctx *c, int party, const uint32_t *ta, double *levkey_out) {
     const int N = c->p.N, H = c->F.H, l = c->p.l_gsw, logB = c->p.logB_gsw;

@@ -86,8 +86,11 @@ void orc_gate_linear(const orc_ctx *c, int op, const uint32_t *in1, const uint32
 /* One iteration of the phase-1 / CGGI loop body on one RLWE row (b, a):
  * acc += ifft(monomial[atilde] * (acc [.] brk[party][idx])).   bootstrapping.jl:47-74, 413-438 */
 void orc_cmux_step(const orc_ctx *c, int party, int idx, uint32_t atilde, void *acc_row /* [2][N] torus */);
+/* One block iteration of the LMSS / KMS_BLOCK loop on one RLWE row (bootstrapping.jl:124-163, 624-655):
+ * at = the ell rotations of block `blk`. */
+void orc_block_step(const orc_ctx *c, int party, int blk, const uint32_t *at, void *acc_row);
 /* KMS / KMS_BLOCK phase 1 for one party (bootstrapping.jl:389-443, 599-659).
- * out: [rows][2][H] complex, rows = 1 for party 0 else l_lev.  max_steps < 0 = all. */
+ * out: [rows][2][H] complex, rows = 1 for party 0 else l_lev. */
 void orc_phase1(const orc_ctx *c, int party, const uint32_t *tildea_party, double *levkey_out);
 /* Test vector + blind rotation: lwe (after the gate's linear part) -> accumulator. */
 void orc_blindrotate(const orc_ctx *c, const uint32_t *lwe, void *acc_out);

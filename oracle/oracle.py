@@ -52,6 +52,8 @@ def lib():
         _lib.orc_modswitch.argtypes = [vp, vp, vp]
         _lib.orc_gate_linear.argtypes = [vp, i32, vp, vp, vp]
         _lib.orc_cmux_step.argtypes = [vp, i32, i32, u32, vp]
+        _lib.orc_block_step.argtypes = [vp, i32, i32, vp, vp]
+        _lib.orc_block_step.restype = None
         _lib.orc_phase1.argtypes = [vp, i32, vp, vp]
         _lib.orc_blindrotate.argtypes = [vp, vp, vp]
         _lib.orc_phase2.argtypes = [vp, vp, u32, vp]
@@ -151,6 +153,11 @@ class Oracle:
     def cmux_step(self, party, idx, atilde, acc_row):
         acc = np.array(acc_row, dtype=self.tdtype, order="C", copy=True)
         lib().orc_cmux_step(self.h, party, idx, int(atilde), _p(acc))
+        return acc
+
+    def block_step(self, party, blk, at, acc_row):
+        acc = np.array(acc_row, dtype=self.tdtype, order="C", copy=True)
+        lib().orc_block_step(self.h, party, blk, _p(np.ascontiguousarray(at, dtype=np.uint32)), _p(acc))
         return acc
 
     def phase1(self, party, tildea_party):

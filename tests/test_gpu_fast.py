@@ -54,7 +54,37 @@ def test_cmux_step_within_tolerance(gpu_schemes, name):
     s.set_mode(MODE_FAST)
 
 
-@pytest.mark.parametrize("name", ["KMS2party"])
+def test_block_step_within_tolerance(gpu_schemes):
+    """KMS_block: one block iteration (3 key bits folded into one accumulator pair in FAST mode) against the oracle's
+    reference-order block step; STRICT is bit-exact."""
+    name = "KMS2partyblock"
+    ks = keyset(name)
+    orc = make_oracle(ks)
+    s = gpu_schemes(name)
+    p = ks.params
+    rng = np.random.default_rng(4)
+    at = np.array([[1, 2, 3], [0, 77, 0], [p.N, 0, 2 * p.N], [4095, 4001, 17], [0, 0, 5], [2 * p.N, 0, 0]], dtype=np.uint32)
+    rows = rng.integers(0, np.iinfo(np.uint64).max, size=(len(at), 2, p.N), dtype=np.uint64)
+    for mode in (MODE_FAST, MODE_STRICT):
+        s.set_mode(mode)
+        worst = 0.0
+        for party, blk in ((0, 0), (1, 5), (1, p.d - 1)):
+            out = s.block_step(party, blk, at, rows)
+            for g in range(len(at)):
+                ref = orc.block_step(party, blk, at[g], rows[g])
+                if mode == MODE_STRICT:
+                    assert np.array_equal(out[g], ref), (party, blk, g)
+                else:
+                    d = np.abs(_signed_diff(out[g], ref)).max()
+                    worst = max(worst, d)
+                    assert d < STEP_TOL, (party, blk, g, np.log2(d + 1))
+            assert np.array_equal(out[5], rows[5])            # only rotation is 2N: exact no-op
+        if mode == MODE_FAST:
+            print(f"worst per-block |delta| = 2^{np.log2(worst + 1):.2f}")
+    s.set_mode(MODE_FAST)
+
+
+@pytest.mark.parametrize("name", ["KMS2party", "KMS2partyblock"])
 def test_fast_gates_decrypt_and_noise(gpu_schemes, name):
     """All six gates over a batch decrypt to the plaintext truth table in FAST mode, identically to STRICT and
     the oracle, and the output phase-error standard deviation matches STRICT mode's."""
