@@ -179,28 +179,26 @@ int run_ccs(mktfhe_ctx *ctx, const uint32_t *tilde, uint32_t *acc, size_t gates)
     return 0;
 }
 
-constexpr int KS_TILE = 16;
-
 int run_keyswitch(mktfhe_ctx *ctx, const void *acc, uint32_t *out, size_t gates) {
     const mktfhe_params &p = ctx->p;
     KsArgs a{};
     a.acc = acc; a.ksk = ctx->d_ksk; a.out = out;
     a.N = ctx->N; a.n = p.n; a.k = p.k; a.f = p.f; a.logD = p.logD; a.Dk = mktfhe_ksk_rows(&p);
-    a.bits64 = ctx->bits == 64; a.block = ctx->block;
-    if (ctx->mode == MKTFHE_MODE_STRICT || p.f * p.logD != 16 || p.logD != 2) {
+    a.bits64 = ctx->bits == 64; a.block = ctx->block; a.rowp = (p.n + 1 + 3) / 4 * 4;
+    if (ctx->mode == MKTFHE_MODE_STRICT || p.f * p.logD != 16 || p.logD != 2 || p.n + 1 > 32 * KS_COLS) {
         // reference loop order: one gate per CTA, parties in sequence
         const size_t smem = keyswitch_smem_bytes(ctx->N, p.f, p.n);
         k_keyswitch<<<(unsigned)gates, MK_THREADS, smem, ctx->stream>>>(a);
     } else {
         CK(cudaMemsetAsync(out, 0, gates * mktfhe_lwe_words(&p) * 4, ctx->stream));
-        const size_t smem = (size_t)ctx->N * KS_TILE * sizeof(uint16_t);
-        const dim3 grid((unsigned)((gates + KS_TILE - 1) / KS_TILE), (unsigned)p.k);
+        const size_t smem = keyswitch_tiled_smem(ctx->N, a.rowp);
+        const dim3 grid((unsigned)((gates + KS_G - 1) / KS_G), (unsigned)p.k, KS_SPLIT);
         if (ctx->block) {
-            CK(cudaFuncSetAttribute(k_keyswitch_tiled<true, KS_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_keyswitch_tiled<true, KS_TILE><<<grid, MK_THREADS, smem, ctx->stream>>>(a, (int)gates);
+            CK(cudaFuncSetAttribute(k_keyswitch_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_keyswitch_tiled<true><<<grid, MK_THREADS, smem, ctx->stream>>>(a, (int)gates);
         } else {
-            CK(cudaFuncSetAttribute(k_keyswitch_tiled<false, KS_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_keyswitch_tiled<false, KS_TILE><<<grid, MK_THREADS, smem, ctx->stream>>>(a, (int)gates);
+            CK(cudaFuncSetAttribute(k_keyswitch_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_keyswitch_tiled<false><<<grid, MK_THREADS, smem, ctx->stream>>>(a, (int)gates);
         }
     }
     ctx->launches++;
@@ -406,7 +404,13 @@ int mktfhe_upload_party_key(mktfhe_ctx *ctx, int party, const double *brk, const
     CK(cudaSetDevice(ctx->device));
     int rc;
     if ((rc = upload(ctx, ctx->brk[party], brk, mktfhe_brk_doubles(&ctx->p) * 8))) return rc;
-    if ((rc = upload(ctx, ctx->ksk[party], ksk, mktfhe_ksk_words(&ctx->p) * 4))) return rc;
+    {   // ksk rows are stored with a 16-byte aligned stride (bulk copies in the tiled key switch)
+        const size_t rows = (size_t)ctx->N * mktfhe_ksk_rows(&ctx->p) * ctx->p.f, row = (size_t)ctx->p.n + 1, rowp = (row + 3) / 4 * 4;
+        dfree(ctx->ksk[party]);
+        CK(cudaMalloc(&ctx->ksk[party], rows * rowp * 4));
+        CK(cudaMemset(ctx->ksk[party], 0, rows * rowp * 4));
+        CK(cudaMemcpy2D(ctx->ksk[party], rowp * 4, ksk, row * 4, row * 4, rows, cudaMemcpyDefault));
+    }
     if (ctx->kms && (rc = upload(ctx, ctx->rlk[party], rlk, mktfhe_rlk_doubles(&ctx->p) * 8))) return rc;
     if (ctx->mk && (rc = upload(ctx, ctx->pubb[party], pubb, mktfhe_pubb_doubles(&ctx->p) * 8))) return rc;
     ctx->finalized = false;

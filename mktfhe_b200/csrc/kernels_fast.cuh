@@ -467,7 +467,7 @@ __device__ __forceinline__ void fft_inv2(cplx (&x)[16], cplx *xa, cplx *xc, cons
     pass1_inv(x);
 }
 
-template <int ELL>
+template <int ELL, int PF>
 __global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, unit_l = tid / UT, t = tid % UT;
@@ -569,15 +569,32 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
                 const cplx *kb = kidx + (size_t)(dg * 2) * H, *ka = kb + H;
                 if (ELL == 1) {
                     cplx wb[16], wa[16];
+                    // PF selects where the key loads are issued: 0 = wb before pass 2, wa before pass 3;
+                    // 1 = wb before pass 3, wa after it; 2 = both after pass 3
                     fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l,
                              [&]() {
+                                 if (PF == 0) {
 #pragma unroll
-                                 for (int e = 0; e < 16; e++) wb[e] = __ldg(kb + e * UT);
+                                     for (int e = 0; e < 16; e++) wb[e] = __ldg(kb + e * UT);
+                                 }
                              },
                              [&]() {
+                                 if (PF == 0) {
 #pragma unroll
-                                 for (int e = 0; e < 16; e++) wa[e] = __ldg(ka + e * UT);
+                                     for (int e = 0; e < 16; e++) wa[e] = __ldg(ka + e * UT);
+                                 } else if (PF == 1) {
+#pragma unroll
+                                     for (int e = 0; e < 16; e++) wb[e] = __ldg(kb + e * UT);
+                                 }
                              });
+                    if (PF == 2) {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) wb[e] = __ldg(kb + e * UT);
+                    }
+                    if (PF >= 1) {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) wa[e] = __ldg(ka + e * UT);
+                    }
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         cplx zb[4], za[4];
@@ -807,8 +824,10 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
     FCK(cudaMemcpy(f.d_brk, f.brk.data(), sizeof(cplx *) * f.brk.size(), cudaMemcpyHostToDevice));
     FCK(cudaFuncSetAttribute(k_phase1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     FCK(cudaFuncSetAttribute(k_phase1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    FCK(cudaFuncSetAttribute(k_phase1_tm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
-    FCK(cudaFuncSetAttribute(k_phase1_tm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
+    FCK(cudaFuncSetAttribute(k_phase1_tm<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
+    FCK(cudaFuncSetAttribute(k_phase1_tm<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
+    FCK(cudaFuncSetAttribute(k_phase1_tm<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
+    FCK(cudaFuncSetAttribute(k_phase1_tm<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
     f.built = true;
     return 0;
 }
@@ -823,8 +842,11 @@ static inline int fast_launch(FastKeys &f, const mktfhe_params &p, fast::Args a,
     a.d = p.d;
     static const bool use_tmem = []() { const char *e = getenv("MKTFHE_FAST_KERNEL"); return !(e && std::string(e) == "smem"); }();
     if (use_tmem) {
-        if (p.scheme == MKTFHE_KMS_BLOCK) k_phase1_tm<3><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
-        else k_phase1_tm<1><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
+        static const int pf = []() { const char *e = getenv("MKTFHE_FAST_PF"); return e ? atoi(e) : 0; }();
+        if (p.scheme == MKTFHE_KMS_BLOCK) k_phase1_tm<3, 0><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
+        else if (pf == 1) k_phase1_tm<1, 1><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
+        else if (pf == 2) k_phase1_tm<1, 2><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
+        else k_phase1_tm<1, 0><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
     } else {
         if (p.scheme == MKTFHE_KMS_BLOCK) k_phase1<3><<<grid, CTA, SMEM_BYTES, stream>>>(a);
         else k_phase1<1><<<grid, CTA, SMEM_BYTES, stream>>>(a);

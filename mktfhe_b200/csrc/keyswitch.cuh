@@ -37,6 +37,7 @@ struct KsArgs {
     const uint32_t *const *ksk;   // [k]: [N][Dk][f][n+1]
     uint32_t *out;                // [B][1 + n*k]
     int N, n, k, f, logD, Dk, bits64, block;
+    int rowp;                     // padded row stride in words (multiple of 4: rows are 16-byte aligned for bulk copies)
 };
 
 // One CTA per gate; parties in sequence; thread tid owns LWE columns tid, tid+256, tid+512 (column 0 = b).
@@ -82,12 +83,12 @@ __global__ void __launch_bounds__(MK_THREADS) k_keyswitch(const KsArgs a) {
         uint32_t sum[MAXC] = {0u, 0u, 0u};
         const uint32_t *ksk = a.ksk[p];
         for (int c = a.block ? n : 0; c < N; c++) {
-            const uint32_t *base = ksk + (size_t)c * a.Dk * f * row;
+            const uint32_t *base = ksk + (size_t)c * a.Dk * f * a.rowp;
 #pragma unroll 4
             for (int lv = 0; lv < f; lv++) {
                 const int d = dig[c * f + lv];
                 if (d == 0) continue;
-                const uint32_t *r = base + ((size_t)((d > 0 ? d : -d) - 1) * f + lv) * row;
+                const uint32_t *r = base + ((size_t)((d > 0 ? d : -d) - 1) * f + lv) * a.rowp;
 #pragma unroll
                 for (int q = 0; q < MAXC; q++) {
                     const int col = tid + q * MK_THREADS;
@@ -108,18 +109,45 @@ __global__ void __launch_bounds__(MK_THREADS) k_keyswitch(const KsArgs a) {
 static inline size_t keyswitch_smem_bytes(int N, int f, int n) { return (size_t)N * f + (size_t)n * 4 + 16; }
 
 // ---------------------------------------------------------------------------------------------------
-// Tiled key switch (production): one CTA = G gates x one party.  All G gates walk (c, level) together, so
-// each selected ksk row is fetched from L2 once per tile and served to the other gates from L1; the digits
-// of the tile are staged in shared memory as 2-bit fields (f*logD = 16 bits per coefficient).
-// Integer adds commute, so the per-party partial sums of b are combined with atomicAdd into a zeroed output.
-template <bool BLOCK, int G>
+// Tiled key switch (production): one CTA = G = 16 gates x one party; warp w owns gates 2w, 2w+1 and lane i owns LWE
+// columns i, i+32, ... of their partial sums (registers).  All gates walk (c, level) together: the Dk candidate ksk
+// rows of a (c, level) are fetched from L2 ONCE per CTA by TMA bulk copies (cp.async.bulk + mbarrier, 4-stage ring in
+// shared memory, issued by one thread) and every gate adds the row its digit selects with conflict-free
+// shared-memory reads -- a warp-uniform choice, so there is no predicated-off work.  Digits of the tile are staged as
+// 2-bit fields (f*logD = 16 bits per coefficient).  Integer adds commute: per-party partial sums of b are combined
+// with atomicAdd into a zeroed output.
+constexpr int KS_G = 16, KS_GW = 2, KS_COLS = 22, KS_STAGES = 6, KS_SPLIT = 2;     // 22 * 32 = 704 >= n + 1 for every set in params.jl
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <bool BLOCK>
 __global__ void __launch_bounds__(MK_THREADS) k_keyswitch_tiled(const KsArgs a, int batch) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint16_t *dig = reinterpret_cast<uint16_t *>(smem_raw);             // [N][G]
-    const int tid = threadIdx.x, p = blockIdx.y, g0 = blockIdx.x * G;
-    const int N = a.N, n = a.n, f = a.f, row = n + 1;
-    constexpr int MAXC = 3;
+    constexpr int G = KS_G, DK = BLOCK ? 2 : 3, S = KS_STAGES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // the coefficient range [c_begin, N) is split over blockIdx.z; each CTA stages only its own coefficients' digits
+    const int c_all = BLOCK ? a.n : 0, c_per = (a.N - c_all + KS_SPLIT - 1) / KS_SPLIT;
+    const int c_begin = c_all + (int)blockIdx.z * c_per, c_end = min(a.N, c_begin + c_per);
+    uint16_t *dig = reinterpret_cast<uint16_t *>(smem_raw);                                  // [c_per][G]
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw + (size_t)((a.N + KS_SPLIT - 1) / KS_SPLIT) * G * sizeof(uint16_t));   // [S][DK][rowp]
+    __shared__ __align__(8) uint64_t full[S];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, p = blockIdx.y, g0 = blockIdx.x * G;
+    const int N = a.N, n = a.n, f = a.f, row = n + 1, rowp = a.rowp;
     const int ng = min(G, batch - g0);
+    const int ncol = (row + 31) / 32;
     auto A = [&](int g, int comp, int c) -> uint32_t {
         const size_t off = ((size_t)(g0 + g) * (a.k + 1) + comp) * N + c;
         return a.bits64 ? (uint32_t)(reinterpret_cast<const uint64_t *>(a.acc)[off] >> 32)
@@ -127,13 +155,17 @@ __global__ void __launch_bounds__(MK_THREADS) k_keyswitch_tiled(const KsArgs a, 
     };
     auto extract = [&](int g, int c) -> uint32_t { return c == 0 ? A(g, 1 + p, 0) : 0u - A(g, 1 + p, N - c); };
 
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     // stage digits: field lv (0 = most significant) of coefficient c sits at bits [2*(f-1-lv), +2)
-    for (int i = tid; i < N * G; i += MK_THREADS) {
-        const int c = i / G, g = i % G;
+    for (int i = tid; i < (c_end - c_begin) * G; i += MK_THREADS) {
+        const int c = c_begin + i / G, g = i % G;
         uint16_t packed = 0;
-        if (g < ng && !(BLOCK && c < n)) {
+        if (g < ng) {
             uint32_t ai = divbits<uint32_t>(extract(g, c), 32 - f * a.logD);
-            if (!BLOCK) packed = (uint16_t)ai;                          // unbalanced digits are the bit fields themselves
+            if (!BLOCK) packed = (uint16_t)ai;                          // unbalanced digits (gsw.jl:34-40) are the bit fields
             else {                                                      // balanced: gsw.jl:42-52, two's-complement 2-bit fields
                 uint32_t acc_bits = 0;
                 for (int lv = f - 1; lv >= 1; lv--) {
@@ -145,75 +177,76 @@ __global__ void __launch_bounds__(MK_THREADS) k_keyswitch_tiled(const KsArgs a, 
                 packed = (uint16_t)acc_bits;
             }
         }
-        dig[c * G + g] = packed;
+        dig[i] = packed;
     }
     __syncthreads();
 
-    uint32_t sum[G][MAXC];
-#pragma unroll
-    for (int g = 0; g < G; g++)
-#pragma unroll
-        for (int q = 0; q < MAXC; q++) sum[g][q] = 0u;
     const uint32_t *ksk = a.ksk[p];
-    const size_t lvl_stride = row, dig_stride = (size_t)f * row;
-    const bool has[MAXC] = {tid < row, tid + MK_THREADS < row, tid + 2 * MK_THREADS < row};
+    const size_t dig_stride = (size_t)f * rowp;
+    const uint32_t row_bytes = (uint32_t)rowp * 4;
+    const int steps = c_end > c_begin ? (c_end - c_begin) * f : 0;
+    auto issue = [&](int it) {              // one thread: DK bulk copies of one padded row each into stage it % S
+        const int c = c_begin + it / f, lv = it % f, s = it % S;
+        const uint32_t *src = ksk + (size_t)c * DK * dig_stride + (size_t)lv * rowp;
+        mbar_expect_tx(&full[s], DK * row_bytes);
+#pragma unroll
+        for (int v = 0; v < DK; v++) tma_bulk_g2s(stage + ((size_t)s * DK + v) * rowp, src + (size_t)v * dig_stride, row_bytes, &full[s]);
+    };
+    if (tid == 0) for (int it = 0; it < S - 1 && it < steps; it++) issue(it);
 
-    // Per (c, level): fetch the Dk candidate rows first (independent coalesced loads, one L2 latency, pipelined across
-    // iterations), then let every gate of the tile pick its row with a warp-uniform branch: no memory operation sits
-    // on the gates' dependency chain.
-    constexpr int DK = BLOCK ? 2 : 3;
-    for (int c = BLOCK ? n : 0; c < N; c++) {
-        const uint32_t *base = ksk + (size_t)c * DK * dig_stride + tid;
-        uint32_t w[G];
+    uint32_t sum[KS_GW][KS_COLS];
 #pragma unroll
-        for (int g = 0; g < G; g++) w[g] = dig[c * G + g];
-#pragma unroll 4
-        for (int lv = 0; lv < f; lv++) {
-            const int sh = 2 * (f - 1 - lv);
-            const uint32_t *lbase = base + lv * lvl_stride;
-            uint32_t x[DK][MAXC];
+    for (int gw = 0; gw < KS_GW; gw++)
 #pragma unroll
-            for (int v = 0; v < DK; v++)
+        for (int j = 0; j < KS_COLS; j++) sum[gw][j] = 0u;
+
+    if (tid == 0 && S - 1 < steps) issue(S - 1);       // (the loop below refills two stages per barrier)
+    for (int it = 0; it < steps; it++) {
+        if ((it & 1) == 0) {
+            __syncthreads();                // every warp is done with steps it - 2, it - 1, whose stages are refilled next
+            if (tid == 0 && it >= 2) {
+                if (it + S - 2 < steps) issue(it + S - 2);
+                if (it + S - 1 < steps) issue(it + S - 1);
+            }
+        }
+        mbar_wait(&full[it % S], (uint32_t)((it / S) & 1));
+        const uint32_t *cur = stage + (size_t)(it % S) * DK * rowp;
+        const int ci = it / f, sh = 2 * (f - 1 - it % f);
 #pragma unroll
-                for (int q = 0; q < MAXC; q++) x[v][q] = has[q] ? __ldg(lbase + (size_t)v * dig_stride + q * MK_THREADS) : 0u;
+        for (int gw = 0; gw < KS_GW; gw++) {
+            const uint32_t d = ((uint32_t)dig[ci * G + warp * KS_GW + gw] >> sh) & 3u;       // uniform over the warp
+            if (d == 0) continue;
+            if (!BLOCK) {
+                const uint32_t *r = cur + (d - 1) * rowp + lane;
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                const uint32_t d = (w[g] >> sh) & 3u;                   // uniform over the CTA
-                if (!BLOCK) {
-                    if (d == 1) {
+                for (int j = 0; j < KS_COLS; j++) if (j < ncol) sum[gw][j] += r[32 * j];
+            } else {                                                    // d = 1: +row 1; d = 3 (-1): -row 1; d = 2 (-2): -row 2
+                const uint32_t *r = cur + (d == 2 ? 1 : 0) * rowp + lane;
+                if (d == 1) {
 #pragma unroll
-                        for (int q = 0; q < MAXC; q++) sum[g][q] += x[0][q];
-                    } else if (d == 2) {
+                    for (int j = 0; j < KS_COLS; j++) if (j < ncol) sum[gw][j] += r[32 * j];
+                } else {
 #pragma unroll
-                        for (int q = 0; q < MAXC; q++) sum[g][q] += x[1][q];
-                    } else if (d == 3) {
-#pragma unroll
-                        for (int q = 0; q < MAXC; q++) sum[g][q] += x[2][q];
-                    }
-                } else {                                                // d = 1: +row 1; d = 3 (-1): -row 1; d = 2 (-2): -row 2
-                    if (d == 1) {
-#pragma unroll
-                        for (int q = 0; q < MAXC; q++) sum[g][q] += x[0][q];
-                    } else if (d == 3) {
-#pragma unroll
-                        for (int q = 0; q < MAXC; q++) sum[g][q] -= x[0][q];
-                    } else if (d == 2) {
-#pragma unroll
-                        for (int q = 0; q < MAXC; q++) sum[g][q] -= x[1][q];
-                    }
+                    for (int j = 0; j < KS_COLS; j++) if (j < ncol) sum[gw][j] -= r[32 * j];
                 }
             }
         }
     }
 #pragma unroll
-    for (int g = 0; g < G; g++) {
-        if (g >= ng) break;
+    for (int gw = 0; gw < KS_GW; gw++) {
+        const int g = warp * KS_GW + gw;
+        if (g >= ng) continue;
         uint32_t *out = a.out + (size_t)(g0 + g) * (1 + (size_t)n * a.k);
 #pragma unroll
-        for (int q = 0; q < MAXC; q++) {
-            const int col = tid + q * MK_THREADS;
-            if (col == 0) atomicAdd(out, sum[g][q] + (p == 0 ? A(g, 0, 0) : 0u));      // res.b = acc.b[0] + sum of parts
-            else if (col < row) out[1 + (size_t)p * n + (col - 1)] = sum[g][q] + ((BLOCK && col - 1 < n) ? extract(g, col - 1) : 0u);
+        for (int j = 0; j < KS_COLS; j++) {
+            const int col = lane + 32 * j;
+            const bool first = blockIdx.z == 0;
+            if (col == 0) atomicAdd(out, sum[gw][j] + (p == 0 && first ? A(g, 0, 0) : 0u));  // res.b = acc.b[0] + sum of parts
+            else if (col < row) atomicAdd(out + 1 + (size_t)p * n + (col - 1), sum[gw][j] + ((BLOCK && first && col - 1 < n) ? extract(g, col - 1) : 0u));
         }
     }
+}
+// digits + S stages of DK rows + slack so that the 32-wide column reads of the last row stay inside the allocation
+static inline size_t keyswitch_tiled_smem(int N, int rowp) {
+    return (size_t)((N + KS_SPLIT - 1) / KS_SPLIT) * KS_G * sizeof(uint16_t) + (size_t)KS_STAGES * 3 * rowp * 4 + 32 * KS_COLS * 4;
 }
