@@ -193,6 +193,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     from mktfhe_b200 import params as P
     from mktfhe_b200.keys import KeySet
@@ -224,7 +232,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": info,
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "reference arm = C port of the reference algorithm (oracle/); Julia is not installed on this image"}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -358,7 +366,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             info, _, _ = cpu_baseline(ks, c1, c2)
             line["cpu_baseline"] = info
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
