@@ -12,6 +12,7 @@
 #include "kernels_strict.cuh"
 #include "keyswitch.cuh"
 #include "kernels_fast.cuh"
+#include "kernels_fast32.cuh"
 
 namespace {
 
@@ -36,6 +37,7 @@ struct mktfhe_ctx {
     uint32_t **d_ksk = nullptr;
     bool finalized = false;
     FastKeys fast;
+    FastKeys32 fast32;
     // workspace for `cap` gates
     size_t cap = 0;
     uint32_t *w_in1 = nullptr, *w_in2 = nullptr, *w_out = nullptr, *w_lin = nullptr, *w_tilde = nullptr, *w_v = nullptr;
@@ -218,9 +220,15 @@ int run_blindrotate(mktfhe_ctx *ctx, const uint32_t *tilde, size_t gates, StageE
         if ((rc = run_ccs(ctx, tilde, (uint32_t *)ctx->w_acc, gates))) return rc;
         if (ev) cudaEventRecord(ev->e[2], ctx->stream);
     } else {
-        RgswArgs a{};
-        a.tilde = tilde; a.acc_io = ctx->w_acc; a.mode = RG_MODE_SK;
-        if ((rc = run_rgsw(ctx, a, gates))) return rc;
+        if (ctx->mode == MKTFHE_MODE_FAST && fast32_supported(p)) {
+            fast32::Args fa{};
+            fa.tilde = tilde; fa.acc_io = (uint32_t *)ctx->w_acc; fa.step_mode = 0; fa.units = gates;
+            if ((rc = fast32_launch(ctx->fast32, p, fa, ctx->stream, &ctx->launches, ctx->err))) return rc;
+        } else {
+            RgswArgs a{};
+            a.tilde = tilde; a.acc_io = ctx->w_acc; a.mode = RG_MODE_SK;
+            if ((rc = run_rgsw(ctx, a, gates))) return rc;
+        }
         if (ev) cudaEventRecord(ev->e[2], ctx->stream);
     }
     return 0;
@@ -376,6 +384,7 @@ void mktfhe_ctx_destroy(mktfhe_ctx *ctx) {
     cudaDeviceSynchronize();
     free_workspace(ctx);
     fast_free(ctx->fast);
+    fast32_free(ctx->fast32);
     for (auto &q : ctx->brk) dfree(q);
     for (auto &q : ctx->rlk) dfree(q);
     for (auto &q : ctx->pubb) dfree(q);
@@ -457,6 +466,7 @@ int mktfhe_finalize_keys(mktfhe_ctx *ctx) {
     }
     CK(cudaGetLastError());
     if (fast_supported(ctx->p) && (rc = fast_build(ctx->fast, ctx->p, ctx->brk, ctx->stream, ctx->err))) return rc;
+    if (fast32_supported(ctx->p) && (rc = fast32_build(ctx->fast32, ctx->p, ctx->brk[0], ctx->stream, ctx->err))) return rc;
     ctx->mode = MKTFHE_MODE_FAST;          // production default; floating-point stages without a FAST kernel run the STRICT one
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->finalized = true;
@@ -630,6 +640,10 @@ static int step_impl(mktfhe_ctx *ctx, int party, int idx, const uint32_t *atilde
     CK(cudaMemcpyAsync(d_rows, acc_rows, batch * row_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->mode == MKTFHE_MODE_FAST && fast_supported(ctx->p) && (block_step == ctx->block)) {
         rc = fast_cmux_step(ctx->fast, ctx->p, party, idx, d_at, d_rows, batch, ctx->stream, &ctx->launches, ctx->err);
+    } else if (ctx->mode == MKTFHE_MODE_FAST && fast32_supported(ctx->p) && (block_step == ctx->block)) {
+        fast32::Args fa{};
+        fa.tilde = d_at; fa.acc_io = (uint32_t *)d_rows; fa.step_mode = block_step ? 2 : 1; fa.step_idx = idx; fa.units = batch;
+        rc = fast32_launch(ctx->fast32, ctx->p, fa, ctx->stream, &ctx->launches, ctx->err);
     } else {
         RgswArgs a{};
         a.tilde = d_at; a.acc_io = d_rows; a.mode = RG_MODE_STEP; a.step_party = party; a.step_idx = idx; a.step_block = block_step;

@@ -1,0 +1,382 @@
+// kernels_fast32.cuh -- FAST-mode blind rotation for the N = 1024, UInt32 single-key schemes:
+//   CGGI  blindrotate!  /root/reference/src/tfhe/bootstrapping.jl:32-76
+//   LMSS  blindrotate!  /root/reference/src/tfhe/bootstrapping.jl:114-165
+// Same construction as kernels_fast.cuh (twist-free product-tree transform, 6-instruction butterflies, fused gadget
+// decomposition, monomial rebuilt per slot, RGSW accumulators in TMEM), sized for H = 512:
+//   unit = one gate = 64 threads x 8 points, passes of 3 + 3 + 3 stages, two double-buffered exchanges;
+//   8 units (16 warps) per CTA, 1 CTA per SM; the RLWE accumulator (8 KiB) stays in shared memory,
+//   the 2 x 8 complex RGSW accumulators per thread in TMEM (32 columns per thread).
+#pragma once
+#include "kernels_fast.cuh"
+
+namespace fast32 {
+
+using fast::bf; using fast::bf_mi; using fast::bi; using fast::bi_mi; using fast::c_e16;
+using fast::tm_ld16; using fast::tm_st16; using fast::tm_wait_ld; using fast::tm_wait_st;
+
+constexpr int H = 512, N = 1024, UT = 64, U = 8, CTA = UT * U;
+constexpr int XB_LEN = H + 64;                       // exchange 2 layout: n + (n >> 3)
+
+__constant__ double2 c_tw1[8];                       // TW[1..7]: stages 1..3
+
+struct Tables {
+    const cplx *t2;        // [4][8]   per 64-point block: w4, w5, w6a, w6b      (TW[8+blk], TW[16+2blk], TW[32+4blk], TW[32+4blk+2])
+    const cplx *t3;        // [4][64]  per thread: TW[64+t], TW[128+2t], TW[256+4t], TW[256+4t+2]
+    const cplx *emono;     // [2048]   exp(-i*pi*m/1024) / H
+};
+
+// stages 1..3: element m of thread t is point t + 64m
+__device__ __forceinline__ void pass1_fwd(cplx (&x)[8]) {
+#pragma unroll
+    for (int m = 0; m < 4; m++) bf(x[m], x[m + 4], c_tw1[1]);
+#pragma unroll
+    for (int m = 0; m < 8; m++) if (!(m & 2)) { if (m & 4) bf_mi(x[m], x[m + 2], c_tw1[2]); else bf(x[m], x[m + 2], c_tw1[2]); }
+#pragma unroll
+    for (int m = 0; m < 8; m += 2) { if (m & 2) bf_mi(x[m], x[m + 1], c_tw1[4 + (m >> 2) * 2]); else bf(x[m], x[m + 1], c_tw1[4 + (m >> 2) * 2]); }
+}
+__device__ __forceinline__ void pass1_inv(cplx (&x)[8]) {
+#pragma unroll
+    for (int m = 0; m < 8; m += 2) { if (m & 2) bi_mi(x[m], x[m + 1], c_tw1[4 + (m >> 2) * 2]); else bi(x[m], x[m + 1], c_tw1[4 + (m >> 2) * 2]); }
+#pragma unroll
+    for (int m = 0; m < 8; m++) if (!(m & 2)) { if (m & 4) bi_mi(x[m], x[m + 2], c_tw1[2]); else bi(x[m], x[m + 2], c_tw1[2]); }
+#pragma unroll
+    for (int m = 0; m < 4; m++) bi(x[m], x[m + 4], c_tw1[1]);
+}
+// stages 4..6 inside 64-point block blk: element q is point 64*blk + o + 8q
+__device__ __forceinline__ void pass2_fwd(cplx (&x)[8], const cplx *__restrict__ tw, int blk) {
+    const cplx w4 = tw[blk], w5 = tw[8 + blk], w6a = tw[16 + blk], w6b = tw[24 + blk];
+#pragma unroll
+    for (int q = 0; q < 4; q++) bf(x[q], x[q + 4], w4);
+#pragma unroll
+    for (int q = 0; q < 8; q++) if (!(q & 2)) { if (q & 4) bf_mi(x[q], x[q + 2], w5); else bf(x[q], x[q + 2], w5); }
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) { const cplx w = (q & 4) ? w6b : w6a; if (q & 2) bf_mi(x[q], x[q + 1], w); else bf(x[q], x[q + 1], w); }
+}
+__device__ __forceinline__ void pass2_inv(cplx (&x)[8], const cplx *__restrict__ tw, int blk) {
+    const cplx w4 = tw[blk], w5 = tw[8 + blk], w6a = tw[16 + blk], w6b = tw[24 + blk];
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) { const cplx w = (q & 4) ? w6b : w6a; if (q & 2) bi_mi(x[q], x[q + 1], w); else bi(x[q], x[q + 1], w); }
+#pragma unroll
+    for (int q = 0; q < 8; q++) if (!(q & 2)) { if (q & 4) bi_mi(x[q], x[q + 2], w5); else bi(x[q], x[q + 2], w5); }
+#pragma unroll
+    for (int q = 0; q < 4; q++) bi(x[q], x[q + 4], w4);
+}
+// stages 7..9 on the 8 contiguous points 8t .. 8t+7: nodes t (depth 6), 2t+{0,1}, 4t+{0..3}
+__device__ __forceinline__ void pass3_fwd(cplx (&x)[8], const cplx *__restrict__ tw, int t) {
+    const cplx w7 = tw[t], w8 = tw[UT + t], w9a = tw[2 * UT + t], w9b = tw[3 * UT + t];
+#pragma unroll
+    for (int e = 0; e < 4; e++) bf(x[e], x[e + 4], w7);
+#pragma unroll
+    for (int e = 0; e < 8; e++) if (!(e & 2)) { if (e & 4) bf_mi(x[e], x[e + 2], w8); else bf(x[e], x[e + 2], w8); }
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) { const cplx w = (e & 4) ? w9b : w9a; if (e & 2) bf_mi(x[e], x[e + 1], w); else bf(x[e], x[e + 1], w); }
+}
+__device__ __forceinline__ void pass3_inv(cplx (&x)[8], const cplx *__restrict__ tw, int t) {
+    const cplx w7 = tw[t], w8 = tw[UT + t], w9a = tw[2 * UT + t], w9b = tw[3 * UT + t];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) { const cplx w = (e & 4) ? w9b : w9a; if (e & 2) bi_mi(x[e], x[e + 1], w); else bi(x[e], x[e + 1], w); }
+#pragma unroll
+    for (int e = 0; e < 8; e++) if (!(e & 2)) { if (e & 4) bi_mi(x[e], x[e + 2], w8); else bi(x[e], x[e + 2], w8); }
+#pragma unroll
+    for (int e = 0; e < 4; e++) bi(x[e], x[e + 4], w7);
+}
+
+__device__ __forceinline__ void unit_bar(int unit) { asm volatile("bar.sync %0, %1;" ::"r"(unit + 1), "r"(UT) : "memory"); }
+
+// Exchange 1 is conflict-free as is (8 consecutive threads touch 8 consecutive elements); exchange 2 is skewed by n >> 3.
+// The two buffers strictly alternate over the whole kernel (xa then xc, forward and inverse alike).
+template <class F>
+__device__ __forceinline__ void fft_fwd(cplx (&x)[8], cplx *xa, cplx *xc, const cplx *tw2, const cplx *tw3, int t, int unit, F mid) {
+    pass1_fwd(x);
+#pragma unroll
+    for (int m = 0; m < 8; m++) xa[t + 64 * m] = x[m];
+    unit_bar(unit);
+    const int blk = t >> 3, o = t & 7;
+#pragma unroll
+    for (int q = 0; q < 8; q++) x[q] = xa[64 * blk + o + 8 * q];
+    mid();
+    pass2_fwd(x, tw2, blk);
+#pragma unroll
+    for (int q = 0; q < 8; q++) xc[72 * blk + o + 9 * q] = x[q];            // n + (n >> 3), n = 64blk + o + 8q
+    unit_bar(unit);
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = xc[9 * t + e];                        // n = 8t + e
+    pass3_fwd(x, tw3, t);
+}
+__device__ __forceinline__ void fft_inv(cplx (&x)[8], cplx *xa, cplx *xc, const cplx *tw2, const cplx *tw3, int t, int unit) {
+    pass3_inv(x, tw3, t);
+#pragma unroll
+    for (int e = 0; e < 8; e++) xa[9 * t + e] = x[e];
+    unit_bar(unit);
+    const int blk = t >> 3, o = t & 7;
+#pragma unroll
+    for (int q = 0; q < 8; q++) x[q] = xa[72 * blk + o + 9 * q];
+    pass2_inv(x, tw2, blk);
+#pragma unroll
+    for (int q = 0; q < 8; q++) xc[64 * blk + o + 8 * q] = x[q];
+    unit_bar(unit);
+#pragma unroll
+    for (int m = 0; m < 8; m++) x[m] = xc[t + 64 * m];
+    pass1_inv(x);
+}
+
+// x mod 2^32 as uint32, rounding toward -inf like `native` (arithmetic.jl:1-4)
+__device__ __forceinline__ uint32_t d2torus32(double x) {
+    const double q = fma(x, 2.3283064365386963e-10, 6755399441055744.0) - 6755399441055744.0;     // rint(x / 2^32)
+    const double y = fma(-4294967296.0, q, x);                                                   // in [-2^31, 2^31]
+    return (uint32_t)__double2ll_rd(y);
+}
+
+struct Args {
+    const uint32_t *tilde;        // [B][lwe_words] / step modes: [units][ELL] rotations
+    const cplx *brk;              // FAST layout [idx][dg][comp][e < 8][t < 64]
+    Tables tb;
+    uint32_t *acc_io;             // out [B][2][N] (step modes: in/out)
+    int step_mode, step_idx;
+    int n, d, l, logB, lwe_words;
+    size_t units;
+};
+
+constexpr size_t SMEM_UNIT = (size_t)2 * N * 4 + (size_t)2 * XB_LEN * 16;       // acc (b, a) + two exchange buffers
+constexpr size_t SMEM_BYTES = U * SMEM_UNIT + (size_t)(32 + 256) * 16 + 16;
+
+template <int ELL>
+__global__ void __launch_bounds__(CTA, 1) k_rgsw_tm(const Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, unit_l = tid / UT, t = tid % UT;
+    cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + U * SMEM_UNIT), *tw3 = tw2 + 32;
+    uint32_t *tm_base_s = reinterpret_cast<uint32_t *>(tw3 + 256);
+    for (int i = tid; i < 256; i += CTA) { if (i < 32) tw2[i] = a.tb.t2[i]; tw3[i] = a.tb.t3[i]; }
+    uint32_t *accb = reinterpret_cast<uint32_t *>(smem_raw + unit_l * SMEM_UNIT), *acca = accb + N;
+    cplx *xa = reinterpret_cast<cplx *>(acca + N), *xc = xa + XB_LEN;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"((uint32_t)__cvta_generic_to_shared(tm_base_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // warp w -> lanes 32*(w%4).., columns 64*(w/4)..; per thread: tacc.b = columns [0,32), tacc.a = [32,64)
+    const uint32_t tm = *tm_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + 64u * (uint32_t)(warp >> 2);
+
+    const size_t unit = (size_t)blockIdx.x * U + unit_l;
+    if (unit < a.units) {
+        const int gate = (int)unit;
+        if (!a.step_mode) {                    // test vector: bootstrapping.jl:11-23
+            const uint32_t tb = a.tilde[(size_t)gate * a.lwe_words];
+            const uint32_t e8 = 1u << 29;
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const uint32_t i1 = (uint32_t)(t + 64 * m) + 1;      // 1-based coefficient index
+                accb[t + 64 * m] = tb <= (uint32_t)N ? (i1 <= tb ? e8 : 0u - e8) : (i1 <= tb - (uint32_t)N ? 0u - e8 : e8);
+                acca[t + 64 * m] = 0u;
+            }
+        } else {
+            const uint32_t *src = a.acc_io + unit * 2 * N;
+#pragma unroll
+            for (int m = 0; m < 16; m++) { accb[t + 64 * m] = src[t + 64 * m]; acca[t + 64 * m] = src[N + t + 64 * m]; }
+        }
+        // thread t only touches coefficients t + 64m of its unit: no barrier needed around the accumulator
+
+        const int l = a.l, logB = a.logB;
+        const int bit = 32 - l * logB;
+        uint32_t cadd = bit > 0 ? 1u << (bit - 1) : 0u;                 // divbits rounding (arithmetic.jl:23-27)
+        for (int j = 0; j < l; j++) cadd += 1u << (bit + j * logB + logB - 1);   // + B/2 at every digit position (gsw.jl:86-96)
+        const uint32_t mask = (1u << logB) - 1;
+        const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));
+        const size_t per_idx = (size_t)4 * l * H;
+        const uint32_t *at_src = a.step_mode ? a.tilde + unit * ELL : a.tilde + (size_t)gate * a.lwe_words + 1;
+        const int nsteps = a.step_mode ? 1 : (ELL == 1 ? a.n : a.d);
+        const int brv6t = (int)(__brev((unsigned)t) >> 26);
+
+        for (int step = 0; step < nsteps; step++) {
+            uint32_t atv[ELL];
+            bool any = false;
+#pragma unroll
+            for (int b = 0; b < ELL; b++) { atv[b] = at_src[(a.step_mode ? 0 : step * ELL) + b]; any |= atv[b] > 0; }
+            if (!any) continue;                                           // :48 / whole-block no-op
+            const int idx = (a.step_mode ? a.step_idx : step) * ELL;
+            const cplx *kidx = a.brk + (size_t)idx * per_idx + t;
+            // slot n = 8t + e evaluates at exp(-i*pi*(4*brv9(n)+1)/N), brv9(n) = 64*brv3(e) + brv6(t)
+            cplx m1v[ELL];
+#pragma unroll
+            for (int b = 0; b < ELL; b++) m1v[b] = __ldg(&a.tb.emono[((4 * brv6t + 1) * atv[b]) & 2047]);
+
+            for (int dg = 0; dg < 2 * l; dg++) {
+                const uint32_t *src = dg < l ? accb : acca;
+                const int sh = bit + (l - 1 - (dg < l ? dg : dg - l)) * logB;
+                cplx x[8];
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    const uint32_t f0 = ((src[t + 64 * m] + cadd) >> sh) & mask, f1 = ((src[t + 64 * m + H] + cadd) >> sh) & mask;
+                    x[m] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
+                }
+                const cplx *kb = kidx + (size_t)(dg * 2) * H, *ka = kb + H;
+                cplx kcb[8], kca[8];
+                if (ELL == 1) {
+                    fft_fwd(x, xa, xc, tw2, tw3, t, unit_l, [&]() {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) { kcb[e] = __ldg(kb + e * UT); kca[e] = __ldg(ka + e * UT); }
+                    });
+                } else {
+                    // block (LMSS): fold the monomials of the block's key bits into the keys,
+                    //   sum_bit mono_bit * (sum_dg D_dg * K_bit,dg) = sum_dg D_dg * (sum_bit mono_bit * K_bit,dg)
+                    fft_fwd(x, xa, xc, tw2, tw3, t, unit_l, []() {});
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int b3 = ((e & 1) << 2) | (e & 2) | ((e & 4) >> 2);
+                        kcb[e] = kca[e] = make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int b = 0; b < ELL; b++) {
+                            if (atv[b] == 0) continue;
+                            cplx mo = cmul_f(m1v[b], c_e16[((atv[b] * b3) & 7) * 2]);
+                            mo.x -= 1.0 / H;
+                            kcb[e] = cmac_f(kcb[e], mo, __ldg(kb + b * per_idx + e * UT));
+                            kca[e] = cmac_f(kca[e], mo, __ldg(ka + b * per_idx + e * UT));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    cplx zb[4], za[4];
+                    if (dg == 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { zb[i] = cmul_f(x[4 * c + i], kcb[4 * c + i]); za[i] = cmul_f(x[4 * c + i], kca[4 * c + i]); }
+                    } else {
+                        fast::tm_ld_c4(tm + 16 * c, zb);
+                        fast::tm_ld_c4(tm + 32 + 16 * c, za);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { zb[i] = cmac_f(zb[i], x[4 * c + i], kcb[4 * c + i]); za[i] = cmac_f(za[i], x[4 * c + i], kca[4 * c + i]); }
+                    }
+                    fast::tm_st_c4(tm + 16 * c, zb);
+                    fast::tm_st_c4(tm + 32 + 16 * c, za);
+                }
+                tm_wait_st();
+            }
+            // both outputs: (x (X^a - 1)/H for ELL == 1) -> inverse transform -> round -> acc +=
+#pragma unroll 1
+            for (int pz = 0; pz < 2; pz++) {
+                cplx y[8];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    cplx z[4];
+                    fast::tm_ld_c4(tm + 32 * pz + 16 * c, z);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) y[4 * c + i] = z[i];
+                }
+                if (ELL == 1) {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int b3 = ((e & 1) << 2) | (e & 2) | ((e & 4) >> 2);
+                        cplx mo = cmul_f(m1v[0], c_e16[((atv[0] * b3) & 7) * 2]);      // 8th roots = even 16th roots
+                        mo.x -= 1.0 / H;
+                        y[e] = cmul_f(mo, y[e]);
+                    }
+                }
+                fft_inv(y, xa, xc, tw2, tw3, t, unit_l);
+                uint32_t *dst = pz == 0 ? accb : acca;
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    dst[t + 64 * m] += d2torus32(y[m].x);
+                    dst[t + 64 * m + H] += d2torus32(-y[m].y);
+                }
+            }
+        }
+        uint32_t *out = a.acc_io + unit * 2 * N;
+#pragma unroll
+        for (int m = 0; m < 16; m++) { out[t + 64 * m] = accb[t + 64 * m]; out[N + t + 64 * m] = acca[t + 64 * m]; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(*tm_base_s));
+}
+
+// reference slot order [poly][8t + e] -> thread order [poly][e][t]
+__global__ void k_permute_brk(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= polys * H) return;
+    const size_t p = i / H;
+    const int r = (int)(i % H), e = r / UT, t = r % UT;
+    out[i] = in[p * H + 8 * t + e];
+}
+
+}  // namespace fast32
+
+struct FastKeys32 {
+    cplx *brk = nullptr, *t2 = nullptr, *t3 = nullptr, *emono = nullptr;
+    bool built = false;
+};
+
+static inline bool fast32_supported(const mktfhe_params &p) {
+    return p.N == 1024 && (p.scheme == MKTFHE_CGGI || (p.scheme == MKTFHE_LMSS && p.ell == 3)) && p.k == 1;
+}
+
+static inline void fast32_free(FastKeys32 &f) {
+    if (f.brk) cudaFree(f.brk);
+    if (f.t2) cudaFree(f.t2);
+    if (f.t3) cudaFree(f.t3);
+    if (f.emono) cudaFree(f.emono);
+    f = FastKeys32();
+}
+
+// Twiddles sqrt(rho(s, i)) = exp(-i*pi*theta(s,i)/2): theta(0,0) = 1/2, theta(s+1, 2i+b) = theta(s,i)/2 + b  (H = 512: 9 stages)
+static inline int fast32_build(FastKeys32 &f, const mktfhe_params &p, const cplx *brk_ref, cudaStream_t stream, std::string &err) {
+    using namespace fast32;
+    fast32_free(f);
+    std::vector<__float128> theta(1, (__float128)0.5);
+    std::vector<cplx> tw(512, make_double2(0.0, 0.0)), t2(32), t3(256), emono(2048), tw1(8, make_double2(0.0, 0.0));
+    const __float128 pi = acosq((__float128)-1);
+    for (int s = 0; s < 9; s++) {
+        std::vector<__float128> nxt(theta.size() * 2);
+        for (size_t i = 0; i < theta.size(); i++) {
+            const __float128 ang = pi * theta[i] / 2;
+            tw[((size_t)1 << s) + i] = make_double2((double)cosq(ang), (double)-sinq(ang));
+            nxt[2 * i] = theta[i] / 2; nxt[2 * i + 1] = theta[i] / 2 + 1;
+        }
+        theta.swap(nxt);
+    }
+    for (int blk = 0; blk < 8; blk++) {
+        t2[blk] = tw[8 + blk]; t2[8 + blk] = tw[16 + 2 * blk]; t2[16 + blk] = tw[32 + 4 * blk]; t2[24 + blk] = tw[32 + 4 * blk + 2];
+    }
+    for (int t = 0; t < 64; t++) {
+        t3[t] = tw[64 + t]; t3[64 + t] = tw[128 + 2 * t]; t3[128 + t] = tw[256 + 4 * t]; t3[192 + t] = tw[256 + 4 * t + 2];
+    }
+    for (int m = 0; m < 2048; m++) {
+        const __float128 ang = pi * m / 1024;
+        emono[m] = make_double2((double)(cosq(ang) / H), (double)(-sinq(ang) / H));
+    }
+    for (int i = 1; i < 8; i++) tw1[i] = tw[i];
+    FCK(cudaMalloc(&f.t2, sizeof(cplx) * 32));
+    FCK(cudaMalloc(&f.t3, sizeof(cplx) * 256));
+    FCK(cudaMalloc(&f.emono, sizeof(cplx) * 2048));
+    FCK(cudaMemcpy(f.t2, t2.data(), sizeof(cplx) * 32, cudaMemcpyHostToDevice));
+    FCK(cudaMemcpy(f.t3, t3.data(), sizeof(cplx) * 256, cudaMemcpyHostToDevice));
+    FCK(cudaMemcpy(f.emono, emono.data(), sizeof(cplx) * 2048, cudaMemcpyHostToDevice));
+    FCK(cudaMemcpyToSymbol(c_tw1, tw1.data(), sizeof(cplx) * 8));
+    {   // the 16th-root table is shared with the N = 2048 kernels
+        std::vector<cplx> e16(16);
+        for (int j = 0; j < 16; j++) { const __float128 ang = pi * j / 8; e16[j] = make_double2((double)cosq(ang), (double)-sinq(ang)); }
+        FCK(cudaMemcpyToSymbol(fast::c_e16, e16.data(), sizeof(cplx) * 16));
+    }
+    const size_t polys = (size_t)p.n * 4 * p.l_gsw;
+    FCK(cudaMalloc(&f.brk, polys * H * sizeof(cplx)));
+    k_permute_brk<<<(unsigned)((polys * H + 255) / 256), 256, 0, stream>>>(brk_ref, f.brk, polys);
+    FCK(cudaGetLastError());
+    FCK(cudaFuncSetAttribute(k_rgsw_tm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    FCK(cudaFuncSetAttribute(k_rgsw_tm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    f.built = true;
+    return 0;
+}
+
+static inline int fast32_launch(FastKeys32 &f, const mktfhe_params &p, fast32::Args a, cudaStream_t stream, int *launches, std::string &err) {
+    using namespace fast32;
+    if (!f.built) { err = "FAST (N = 1024) keys not built"; return -3; }
+    a.brk = f.brk; a.tb = Tables{f.t2, f.t3, f.emono};
+    a.n = p.n; a.d = p.d; a.l = p.l_gsw; a.logB = p.logB_gsw; a.lwe_words = (int)mktfhe_lwe_words(&p);
+    const unsigned grid = (unsigned)((a.units + U - 1) / U);
+    if (p.scheme == MKTFHE_LMSS && !(a.step_mode == 1)) k_rgsw_tm<3><<<grid, CTA, SMEM_BYTES, stream>>>(a);
+    else k_rgsw_tm<1><<<grid, CTA, SMEM_BYTES, stream>>>(a);
+    if (launches) (*launches)++;
+    FCK(cudaGetLastError());
+    return 0;
+}
