@@ -44,7 +44,7 @@ WORKLOADS = {  # name -> (parameter set, default per-GPU batch)
     "cggi": ("CGGIparam", 4096),
     "lmss": ("Blockparam", 4096),
     "ccs2": ("CCS2party", 1024),
-    "ccs16": ("CCS16party", 64),
+    "ccs16": ("CCS16party", 592),
 }
 
 

@@ -38,6 +38,7 @@ struct mktfhe_ctx {
     bool finalized = false;
     FastKeys fast;
     FastKeys32 fast32;
+    FastCcsKeys fastccs;
     // workspace for `cap` gates
     size_t cap = 0;
     uint32_t *w_in1 = nullptr, *w_in2 = nullptr, *w_out = nullptr, *w_lin = nullptr, *w_tilde = nullptr, *w_v = nullptr;
@@ -217,7 +218,11 @@ int run_blindrotate(mktfhe_ctx *ctx, const uint32_t *tilde, size_t gates, StageE
         if (ev) cudaEventRecord(ev->e[2], ctx->stream);
         if ((rc = run_phase2(ctx, tilde, ctx->w_lev, (uint64_t *)ctx->w_acc, gates))) return rc;
     } else if (p.scheme == MKTFHE_CCS) {
-        if ((rc = run_ccs(ctx, tilde, (uint32_t *)ctx->w_acc, gates))) return rc;
+        if (ctx->mode == MKTFHE_MODE_FAST && fastccs_supported(p))
+            rc = fastccs_launch(ctx->fastccs, ctx->fast32, p, tilde, (uint32_t *)ctx->w_acc, ctx->w_tx, gates, ctx->stream, &ctx->launches, ctx->err);
+        else
+            rc = run_ccs(ctx, tilde, (uint32_t *)ctx->w_acc, gates);
+        if (rc) return rc;
         if (ev) cudaEventRecord(ev->e[2], ctx->stream);
     } else {
         if (ctx->mode == MKTFHE_MODE_FAST && fast32_supported(p)) {
@@ -385,6 +390,7 @@ void mktfhe_ctx_destroy(mktfhe_ctx *ctx) {
     free_workspace(ctx);
     fast_free(ctx->fast);
     fast32_free(ctx->fast32);
+    fastccs_free(ctx->fastccs);
     for (auto &q : ctx->brk) dfree(q);
     for (auto &q : ctx->rlk) dfree(q);
     for (auto &q : ctx->pubb) dfree(q);
@@ -467,6 +473,10 @@ int mktfhe_finalize_keys(mktfhe_ctx *ctx) {
     CK(cudaGetLastError());
     if (fast_supported(ctx->p) && (rc = fast_build(ctx->fast, ctx->p, ctx->brk, ctx->stream, ctx->err))) return rc;
     if (fast32_supported(ctx->p) && (rc = fast32_build(ctx->fast32, ctx->p, ctx->brk[0], ctx->stream, ctx->err))) return rc;
+    if (fastccs_supported(ctx->p)) {
+        if ((rc = fast32_build(ctx->fast32, ctx->p, nullptr, ctx->stream, ctx->err))) return rc;      // transform tables only
+        if ((rc = fastccs_build(ctx->fastccs, ctx->p, ctx->brk, ctx->pubb, ctx->crs, ctx->stream, ctx->err))) return rc;
+    }
     ctx->mode = MKTFHE_MODE_FAST;          // production default; floating-point stages without a FAST kernel run the STRICT one
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->finalized = true;

@@ -358,10 +358,12 @@ static inline int fast32_build(FastKeys32 &f, const mktfhe_params &p, const cplx
         for (int j = 0; j < 16; j++) { const __float128 ang = pi * j / 8; e16[j] = make_double2((double)cosq(ang), (double)-sinq(ang)); }
         FCK(cudaMemcpyToSymbol(fast::c_e16, e16.data(), sizeof(cplx) * 16));
     }
-    const size_t polys = (size_t)p.n * 4 * p.l_gsw;
-    FCK(cudaMalloc(&f.brk, polys * H * sizeof(cplx)));
-    k_permute_brk<<<(unsigned)((polys * H + 255) / 256), 256, 0, stream>>>(brk_ref, f.brk, polys);
-    FCK(cudaGetLastError());
+    if (brk_ref) {
+        const size_t polys = (size_t)p.n * 4 * p.l_gsw;
+        FCK(cudaMalloc(&f.brk, polys * H * sizeof(cplx)));
+        k_permute_brk<<<(unsigned)((polys * H + 255) / 256), 256, 0, stream>>>(brk_ref, f.brk, polys);
+        FCK(cudaGetLastError());
+    }
     FCK(cudaFuncSetAttribute(k_rgsw_tm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     FCK(cudaFuncSetAttribute(k_rgsw_tm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     f.built = true;
@@ -376,6 +378,226 @@ static inline int fast32_launch(FastKeys32 &f, const mktfhe_params &p, fast32::A
     const unsigned grid = (unsigned)((a.units + U - 1) / U);
     if (p.scheme == MKTFHE_LMSS && !(a.step_mode == 1)) k_rgsw_tm<3><<<grid, CTA, SMEM_BYTES, stream>>>(a);
     else k_rgsw_tm<1><<<grid, CTA, SMEM_BYTES, stream>>>(a);
+    if (launches) (*launches)++;
+    FCK(cudaGetLastError());
+    return 0;
+}
+
+// ======================================================================================================
+// CCS blind rotation, FAST mode: /root/reference/src/tfhe/bootstrapping.jl:234-328.
+// One unit = one gate = 64 threads x 8 points (the transform above), 4 units per CTA.  Per (party, key bit) step the
+// hybrid product is evaluated component by component, everything of a component staying in registers:
+//   u_c  = sum_j D_j(acc_c) * d[j]                                   (:277-284)
+//   v_c  = -/+ sum_j D_j(acc_c) * (crs[j] | b_{c-1}[j])              (:286-294)   -> inverse -> 32-bit coefficients
+//   w   += sum_j D_j(v_c) * f[j]                                     (:313-320)   (two running accumulators)
+// and finally acc_c += ifft(monomial * (u_c [+ w])) for the live components (:322-324).  The accumulator polynomials
+// and the u_c live in global memory (L2-resident: (k+1) x 4 KiB + (k+1) x 8 KiB per gate); keys are read through L1,
+// which the four gates of a CTA share because they walk the (party, bit) steps together.
+// FAST order of the floating-point sums differs from the reference (the w terms are accumulated before u_0 / u_na
+// are added); integer stages are the reference's.
+namespace fast32 {
+
+constexpr int CU = 4, CCTA = UT * CU;
+
+struct CcsArgs {
+    const uint32_t *tilde;          // [B][lwe_words]
+    const cplx *const *brk;         // [k] FAST layout [n][lu][3][e][t]
+    const cplx *const *pubb;        // [k] FAST layout [lu][e][t], scaled by 1/H
+    const cplx *crs;                // FAST layout [lu][e][t], scaled by 1/H
+    Tables tb;
+    uint32_t *acc;                  // [B][(k+1)][N]
+    cplx *tacc;                     // scratch [B][(k+1)][H], thread layout
+    int n, k, lu, logB, lwe_words;
+    size_t units;
+};
+
+constexpr size_t CCS_SMEM_UNIT = (size_t)2 * XB_LEN * 16;
+constexpr size_t CCS_SMEM_BYTES = CU * CCS_SMEM_UNIT + (size_t)(32 + 256) * 16;
+
+__global__ void __launch_bounds__(CCTA, 1) k_ccs_fast(const CcsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, unit_l = tid / UT, t = tid % UT;
+    cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + CU * CCS_SMEM_UNIT), *tw3 = tw2 + 32;
+    for (int i = tid; i < 256; i += CCTA) { if (i < 32) tw2[i] = a.tb.t2[i]; tw3[i] = a.tb.t3[i]; }
+    cplx *xa = reinterpret_cast<cplx *>(smem_raw + unit_l * CCS_SMEM_UNIT), *xc = xa + XB_LEN;
+    __syncthreads();
+
+    const size_t unit = (size_t)blockIdx.x * CU + unit_l;
+    const bool live = unit < a.units;
+    const size_t g = live ? unit : 0;
+    const int k = a.k, lu = a.lu, logB = a.logB;
+    uint32_t *ACC = a.acc + g * (size_t)(k + 1) * N;
+    cplx *TACC = a.tacc + g * (size_t)(k + 1) * H;
+    const uint32_t *tilde = a.tilde + g * a.lwe_words;
+
+    if (live) {                                     // test vector (bootstrapping.jl:11-23), a components zero
+        const uint32_t tb = tilde[0], e8 = 1u << 29;
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const uint32_t i1 = (uint32_t)(t + 64 * m) + 1;
+            ACC[t + 64 * m] = tb <= (uint32_t)N ? (i1 <= tb ? e8 : 0u - e8) : (i1 <= tb - (uint32_t)N ? 0u - e8 : e8);
+        }
+        for (int c = 1; c <= k; c++)
+#pragma unroll
+            for (int m = 0; m < 16; m++) ACC[(size_t)c * N + t + 64 * m] = 0u;
+    }
+    const int bit = 32 - lu * logB;
+    uint32_t cadd = bit > 0 ? 1u << (bit - 1) : 0u;
+    for (int j = 0; j < lu; j++) cadd += 1u << (bit + j * logB + logB - 1);
+    const uint32_t mask = (1u << logB) - 1;
+    const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));
+    const int brv6t = (int)(__brev((unsigned)t) >> 26);
+    const size_t tile = (size_t)H;                  // one key polynomial
+
+    // digit j of 16 cached coefficients (8 low, 8 at +H) -> 8 complex points
+    auto digits = [&](const uint32_t (&cf)[16], int j, cplx (&x)[8]) {
+        const int sh = bit + (lu - 1 - j) * logB;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const uint32_t f0 = ((cf[m] + cadd) >> sh) & mask, f1 = ((cf[m + 8] + cadd) >> sh) & mask;
+            x[m] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
+        }
+    };
+
+    for (int idx = 0; idx < k; idx++) {
+        const int na = idx + 1;                                     // live a-components a_1 .. a_na
+        for (int i = 0; i < a.n; i++) {
+            __syncthreads();                                        // the gates of a CTA walk the steps together (L1 key reuse)
+            const uint32_t at = live ? tilde[1 + (size_t)idx * a.n + i] : 0u;
+            if (at == 0) continue;                                  // :262
+            const cplx *uni = a.brk[idx] + (size_t)i * 3 * lu * tile + t;      // [j][d, f.b, f.a][e][t]
+            cplx wb[8], wa[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) wb[e] = wa[e] = make_double2(0.0, 0.0);
+
+            for (int c = 0; c <= na; c++) {
+                uint32_t cf[16];
+#pragma unroll
+                for (int m = 0; m < 8; m++) { cf[m] = ACC[(size_t)c * N + t + 64 * m]; cf[m + 8] = ACC[(size_t)c * N + t + 64 * m + H]; }
+                cplx u[8], v[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) u[e] = v[e] = make_double2(0.0, 0.0);
+                const cplx *kv = (c == 0 ? a.crs : a.pubb[c - 1]) + t;
+                for (int j = 0; j < lu; j++) {
+                    cplx x[8], kd[8], kw[8];
+                    digits(cf, j, x);
+                    fft_fwd(x, xa, xc, tw2, tw3, t, unit_l, [&]() {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) { kd[e] = __ldg(uni + (size_t)(j * 3) * tile + e * UT); kw[e] = __ldg(kv + (size_t)j * tile + e * UT); }
+                    });
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { u[e] = cmac_f(u[e], x[e], kd[e]); v[e] = cmac_f(v[e], x[e], kw[e]); }
+                }
+                if (c == 0) {                                       // v0 = - sum (mulsubto!, :288-290)
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] = make_double2(-v[e].x, -v[e].y);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; e++) TACC[(size_t)c * H + e * UT + t] = u[e];
+                fft_inv(v, xa, xc, tw2, tw3, t, unit_l);            // crs / pubb carry the 1/H
+#pragma unroll
+                for (int m = 0; m < 8; m++) { cf[m] = d2torus32(v[m].x); cf[m + 8] = d2torus32(-v[m].y); }
+                for (int j = 0; j < lu; j++) {
+                    cplx x[8], kb[8], ka[8];
+                    digits(cf, j, x);
+                    fft_fwd(x, xa, xc, tw2, tw3, t, unit_l, [&]() {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) { kb[e] = __ldg(uni + (size_t)(j * 3 + 1) * tile + e * UT); ka[e] = __ldg(uni + (size_t)(j * 3 + 2) * tile + e * UT); }
+                    });
+#pragma unroll
+                    for (int e = 0; e < 8; e++) { wb[e] = cmac_f(wb[e], x[e], kb[e]); wa[e] = cmac_f(wa[e], x[e], ka[e]); }
+                }
+            }
+            // acc_c += ifft(monomial * tacc_c); tacc_0 = u_0 + w_b, tacc_na = u_na + w_a  (:322-324)
+            const cplx m1 = __ldg(&a.tb.emono[((4 * brv6t + 1) * at) & 2047]);
+            for (int c = 0; c <= na; c++) {
+                cplx y[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    y[e] = TACC[(size_t)c * H + e * UT + t];
+                    if (c == 0) { y[e].x += wb[e].x; y[e].y += wb[e].y; }
+                    if (c == na) { y[e].x += wa[e].x; y[e].y += wa[e].y; }
+                    const int b3 = ((e & 1) << 2) | (e & 2) | ((e & 4) >> 2);
+                    cplx mo = cmul_f(m1, c_e16[((at * b3) & 7) * 2]);
+                    mo.x -= 1.0 / H;
+                    y[e] = cmul_f(mo, y[e]);
+                }
+                fft_inv(y, xa, xc, tw2, tw3, t, unit_l);
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    ACC[(size_t)c * N + t + 64 * m] += d2torus32(y[m].x);
+                    ACC[(size_t)c * N + t + 64 * m + H] += d2torus32(-y[m].y);
+                }
+            }
+        }
+    }
+}
+
+// reference slot order -> thread order, with an optional scale (1/H for the keys that feed an inverse transform)
+__global__ void k_permute_scale(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys, double scale) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= polys * H) return;
+    const size_t p = i / H;
+    const int r = (int)(i % H), e = r / UT, t = r % UT;
+    const cplx z = in[p * H + 8 * t + e];
+    out[i] = make_double2(z.x * scale, z.y * scale);
+}
+
+}  // namespace fast32
+
+struct FastCcsKeys {
+    std::vector<cplx *> brk, pubb;
+    cplx **d_brk = nullptr, **d_pubb = nullptr, *crs = nullptr;
+    bool built = false;
+};
+
+static inline bool fastccs_supported(const mktfhe_params &p) { return p.scheme == MKTFHE_CCS && p.N == 1024; }
+
+static inline void fastccs_free(FastCcsKeys &f) {
+    for (auto &q : f.brk) if (q) cudaFree(q);
+    for (auto &q : f.pubb) if (q) cudaFree(q);
+    if (f.d_brk) cudaFree(f.d_brk);
+    if (f.d_pubb) cudaFree(f.d_pubb);
+    if (f.crs) cudaFree(f.crs);
+    f = FastCcsKeys();
+}
+
+static inline int fastccs_build(FastCcsKeys &f, const mktfhe_params &p, const std::vector<cplx *> &brk_ref, const std::vector<cplx *> &pubb_ref,
+                                const cplx *crs_ref, cudaStream_t stream, std::string &err) {
+    using namespace fast32;
+    fastccs_free(f);
+    const size_t brk_polys = (size_t)p.n * 3 * p.l_uni, small = (size_t)p.l_uni;
+    auto perm = [&](const cplx *src, cplx **dst, size_t polys, double scale) -> int {
+        FCK(cudaMalloc(dst, polys * H * sizeof(cplx)));
+        k_permute_scale<<<(unsigned)((polys * H + 255) / 256), 256, 0, stream>>>(src, *dst, polys, scale);
+        FCK(cudaGetLastError());
+        return 0;
+    };
+    f.brk.assign(brk_ref.size(), nullptr); f.pubb.assign(brk_ref.size(), nullptr);
+    int rc;
+    for (size_t i = 0; i < brk_ref.size(); i++) {
+        if ((rc = perm(brk_ref[i], &f.brk[i], brk_polys, 1.0))) return rc;
+        if ((rc = perm(pubb_ref[i], &f.pubb[i], small, 1.0 / H))) return rc;
+    }
+    if ((rc = perm(crs_ref, &f.crs, small, 1.0 / H))) return rc;
+    FCK(cudaMalloc(&f.d_brk, sizeof(cplx *) * f.brk.size()));
+    FCK(cudaMalloc(&f.d_pubb, sizeof(cplx *) * f.pubb.size()));
+    FCK(cudaMemcpy(f.d_brk, f.brk.data(), sizeof(cplx *) * f.brk.size(), cudaMemcpyHostToDevice));
+    FCK(cudaMemcpy(f.d_pubb, f.pubb.data(), sizeof(cplx *) * f.pubb.size(), cudaMemcpyHostToDevice));
+    FCK(cudaFuncSetAttribute(k_ccs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CCS_SMEM_BYTES));
+    f.built = true;
+    return 0;
+}
+
+static inline int fastccs_launch(FastCcsKeys &f, FastKeys32 &tabs, const mktfhe_params &p, const uint32_t *tilde, uint32_t *acc, cplx *tacc,
+                                 size_t gates, cudaStream_t stream, int *launches, std::string &err) {
+    using namespace fast32;
+    if (!f.built || !tabs.t2) { err = "FAST CCS keys not built"; return -3; }
+    fast32::CcsArgs a{};
+    a.tilde = tilde; a.brk = f.d_brk; a.pubb = f.d_pubb; a.crs = f.crs; a.tb = Tables{tabs.t2, tabs.t3, tabs.emono};
+    a.acc = acc; a.tacc = tacc; a.n = p.n; a.k = p.k; a.lu = p.l_uni; a.logB = p.logB_uni; a.lwe_words = (int)mktfhe_lwe_words(&p);
+    a.units = gates;
+    k_ccs_fast<<<(unsigned)((gates + CU - 1) / CU), CCTA, CCS_SMEM_BYTES, stream>>>(a);
     if (launches) (*launches)++;
     FCK(cudaGetLastError());
     return 0;

@@ -137,7 +137,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 template <bool BLOCK>
 __global__ void __launch_bounds__(MK_THREADS) k_keyswitch_tiled(const KsArgs a, int batch) {
     constexpr int G = KS_G, DK = BLOCK ? 2 : 3, S = KS_STAGES;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     // the coefficient range [c_begin, N) is split over blockIdx.z; each CTA stages only its own coefficients' digits
     const int c_all = BLOCK ? a.n : 0, c_per = (a.N - c_all + KS_SPLIT - 1) / KS_SPLIT;
     const int c_begin = c_all + (int)blockIdx.z * c_per, c_end = min(a.N, c_begin + c_per);

@@ -95,7 +95,7 @@ def test_block_step_within_tolerance(gpu_schemes, name):
     s.set_mode(MODE_FAST)
 
 
-@pytest.mark.parametrize("name", ["KMS2party", "KMS2partyblock", "CGGIparam", "Blockparam"])
+@pytest.mark.parametrize("name", ["KMS2party", "KMS2partyblock", "CGGIparam", "Blockparam", "CCS2party"])
 def test_fast_gates_decrypt_and_noise(gpu_schemes, name):
     """All six gates over a batch decrypt to the plaintext truth table in FAST mode, identically to STRICT and
     the oracle, and the output phase-error standard deviation matches STRICT mode's."""

@@ -26,6 +26,28 @@ def test_larger_party_counts(gpu_schemes, name):
     assert np.array_equal(s.gate(0, c1[:1], c2[:1])[0], orc.bootstrap(lin))
     acc = s.blindrotate(lin[None])[0]
     assert np.array_equal(acc, orc.blindrotate(lin))
+    if name.startswith("CCS"):
+        # CCS4party sits at the edge of its noise budget in the reference algorithm itself: the oracle-identical STRICT
+        # path decrypts ~96 % of fresh NANDs (output error std 2^28.07 against a margin of 2^29).  Production mode
+        # must show the same statistics, not exact decryptions.
+        stats = {}
+        for mode in (MODE_STRICT, MODE_FAST):
+            s.set_mode(mode)
+            errs, ok = [], 0
+            for op in (0, 3, 5):
+                out = s.gate(op, c1, c2)
+                want = np.array([PLAIN[op](bool(x), bool(y)) for x, y in zip(b1, b2)])
+                ok += int(np.sum(ks.decrypt_batch(out) == want))
+                for g in range(B):
+                    e = (ks.phase(out[g]) - ((1 << 29) if want[g] else (7 << 29))) & 0xFFFFFFFF
+                    errs.append(e - (1 << 32) if e >= (1 << 31) else e)
+            stats[mode] = (ok, float(np.std(errs)))
+        print(f"{name}: STRICT ok {stats[MODE_STRICT][0]}/{3 * B} std 2^{np.log2(stats[MODE_STRICT][1]):.2f}; "
+              f"FAST ok {stats[MODE_FAST][0]}/{3 * B} std 2^{np.log2(stats[MODE_FAST][1]):.2f}")
+        assert 0.75 < stats[MODE_FAST][1] / stats[MODE_STRICT][1] < 1.33
+        assert stats[MODE_FAST][0] >= 0.85 * 3 * B and stats[MODE_STRICT][0] >= 0.85 * 3 * B
+        s.set_mode(MODE_FAST)
+        return
     # production mode: all gates over the batch
     s.set_mode(MODE_FAST)
     worst = 0
@@ -38,10 +60,6 @@ def test_larger_party_counts(gpu_schemes, name):
             worst = max(worst, abs(e - (1 << 32) if e >= (1 << 31) else e))
     print(f"{name}: worst |phase error| = 2^{np.log2(worst + 1):.2f} (margin 2^29)")
     assert worst < (1 << 29)
-    if name.startswith("CCS"):
-        # CCS noise grows quadratically in k (its output std is already ~2^27 at k = 4): second-level gates fail with
-        # visible probability in the reference algorithm itself, so only the first level is asserted for CCS.
-        return
     # chained gates: outputs of bootstraps feed the next level (full-support ciphertexts)
     lvl = s.gate(0, c1, c2)
     lvl2 = s.gate(2, lvl, c1)
