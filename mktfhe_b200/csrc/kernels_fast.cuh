@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1(const Args a) {
 }
 
 // ======================================================================================================
-// TMEM variant (default).  Blackwell's tensor memory is lane-private per warp quadrant, which is exactly the
+// TMEM variant (MKTFHE_FAST_KERNEL=tmem).  Blackwell's tensor memory is lane-private per warp quadrant, which is exactly the
 // ownership pattern of this kernel: thread t only ever touches RLWE-accumulator coefficients t + 64m (+H) and
 // RGSW-accumulator slots 16t + e.  Both accumulators therefore live in TMEM (tcgen05.ld / tcgen05.st,
 // measured ~850 B/clk/SM against 128 B/clk/SM for shared memory):
@@ -467,7 +467,7 @@ __device__ __forceinline__ void fft_inv2(cplx (&x)[16], cplx *xa, cplx *xc, cons
     pass1_inv(x);
 }
 
-template <int ELL, int PF>
+template <int ELL>
 __global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, unit_l = tid / UT, t = tid % UT;
@@ -569,32 +569,16 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
                 const cplx *kb = kidx + (size_t)(dg * 2) * H, *ka = kb + H;
                 if (ELL == 1) {
                     cplx wb[16], wa[16];
-                    // PF selects where the key loads are issued: 0 = wb before pass 2, wa before pass 3;
-                    // 1 = wb before pass 3, wa after it; 2 = both after pass 3
+                    // key values are requested before the passes that precede their use
                     fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l,
                              [&]() {
-                                 if (PF == 0) {
 #pragma unroll
-                                     for (int e = 0; e < 16; e++) wb[e] = __ldg(kb + e * UT);
-                                 }
+                                 for (int e = 0; e < 16; e++) wb[e] = __ldg(kb + e * UT);
                              },
                              [&]() {
-                                 if (PF == 0) {
 #pragma unroll
-                                     for (int e = 0; e < 16; e++) wa[e] = __ldg(ka + e * UT);
-                                 } else if (PF == 1) {
-#pragma unroll
-                                     for (int e = 0; e < 16; e++) wb[e] = __ldg(kb + e * UT);
-                                 }
+                                 for (int e = 0; e < 16; e++) wa[e] = __ldg(ka + e * UT);
                              });
-                    if (PF == 2) {
-#pragma unroll
-                        for (int e = 0; e < 16; e++) wb[e] = __ldg(kb + e * UT);
-                    }
-                    if (PF >= 1) {
-#pragma unroll
-                        for (int e = 0; e < 16; e++) wa[e] = __ldg(ka + e * UT);
-                    }
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         cplx zb[4], za[4];
@@ -732,6 +716,320 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tm_base_s));
 }
 
+// ======================================================================================================
+// TMA variant (default): the TMEM kernel above with the bootstrapping key streamed ONCE PER CTA.
+// The four units of a CTA are chosen from the same party, so they consume the same key polynomials in the same order
+// (only their rotations differ).  A ninth warp is the producer: one thread walks the tile sequence
+//   (step, [bit], digit, comp)  ->  16 KiB polynomial in thread order
+// and issues `cp.async.bulk` copies into a 5-slot shared-memory ring guarded by full/empty mbarriers; the 256
+// consumer threads read their 16 values of a tile with conflict-free 16-byte loads and release the slot.
+// Effect: L2 -> SM key traffic drops 4x (it was 1.3 TB per 4096-gate launch, 5.4 TB/s), key values no longer occupy
+// 128 registers per thread, and their latency is hidden by the ring instead of by the scheduler.
+constexpr int RING = 5, TILE = H;                                        // tile = one polynomial, 16 KiB
+constexpr int CTA_TMA = CTA + 128;                                   // 2 consumer warpgroups + 1 producer warpgroup
+constexpr size_t SMEM_BYTES_TMA = U * SMEM_UNIT_TM + (size_t)(128 + 128 + 256) * 16 + (size_t)RING * TILE * 16 + 128;
+
+__device__ __forceinline__ void mb_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int ELL>
+__global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, unit_l = tid / UT, t = tid % UT;
+    cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + U * SMEM_UNIT_TM), *tw8 = tw2 + 128, *tw9e = tw8 + 128;
+    cplx *ring = tw9e + 256;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)RING * TILE), *empty = full + RING;
+    uint32_t *tm_base_s = reinterpret_cast<uint32_t *>(empty + RING);
+    for (int i = tid; i < 256; i += CTA_TMA) { if (i < 128) { tw2[i] = a.tb.t2[i]; tw8[i] = a.tb.t8[i]; } tw9e[i] = a.tb.t9[i]; }
+    if (tid == 0) {
+        for (int s = 0; s < RING; s++) { mb_init(&full[s], 1); mb_init(&empty[s], CTA); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"((uint32_t)__cvta_generic_to_shared(tm_base_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    // ---- CTA -> (party, units): party 0 has one RLEV row per gate, the others l_lev (bootstrapping.jl:400)
+    int party, rows;
+    size_t u0;                                                     // first unit (within the party) of this CTA
+    size_t gates;
+    if (!a.step_mode) {
+        gates = a.units / a.R;
+        const size_t ctas0 = (gates + U - 1) / U, ctasp = (gates * a.l_lev + U - 1) / U;
+        if (blockIdx.x < ctas0) { party = 0; rows = 1; u0 = (size_t)blockIdx.x * U; }
+        else { party = 1 + (int)((blockIdx.x - ctas0) / ctasp); rows = a.l_lev; u0 = ((blockIdx.x - ctas0) % ctasp) * U; }
+    } else { gates = a.units; party = a.step_party; rows = 1; u0 = (size_t)blockIdx.x * U; }
+    const int l = a.l;
+    const size_t per_idx = (size_t)4 * l * H;
+    const int nsteps = a.step_mode ? 1 : (ELL == 1 ? a.n : a.d);
+    const cplx *brk = a.brk[party];
+    const uint32_t ntiles = (uint32_t)nsteps * 2 * l * ELL * 2;
+
+    // The register file is partitioned per scheduler (16K registers each), so a ninth warp at 200+ registers does not
+    // fit: the CTA is launched with 12 warps at <= 168 registers and the warpgroups re-split the pool (setmaxnreg):
+    // the producer warpgroup keeps 24 registers per thread, the two consumer warpgroups take 232.
+    if (warp >= U * 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        // ---- producer: tile n = (((step * 2l + dg) * ELL + b) * 2 + comp)
+        if (tid == CTA) {
+            for (uint32_t n = 0; n < ntiles; n++) {
+                const int slot = n % RING;
+                if (n >= RING) mb_wait(&empty[slot], ((n / RING) - 1) & 1);
+                const uint32_t comp = n & 1, b = (n >> 1) % ELL, dg = ((n >> 1) / ELL) % (2 * l), step = (n >> 1) / ELL / (2 * l);
+                const int idx = (a.step_mode ? a.step_idx : (int)step) * ELL + (int)b;
+                mb_expect_tx(&full[slot], TILE * 16);
+                bulk_g2s(ring + (size_t)slot * TILE, brk + (size_t)idx * per_idx + (size_t)(dg * 2 + comp) * H, TILE * 16, &full[slot]);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        // ---- consumers
+        const uint32_t tm = *tm_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + 256u * (uint32_t)(warp >> 2);
+        cplx *xa = reinterpret_cast<cplx *>(smem_raw + unit_l * SMEM_UNIT_TM), *xc = xa + XB_LEN;
+        const size_t up = u0 + unit_l;                             // unit index inside the party
+        const bool live = up < gates * (size_t)rows;
+        const int gate = live ? (int)(up / rows) : 0, row = live ? (int)(up % rows) : 0;
+        const size_t unit_out = a.step_mode ? up : (size_t)gate * a.R + (party == 0 ? 0 : 1 + (size_t)(party - 1) * a.l_lev + row);
+        uint32_t tile_n = 0;                                       // next tile this thread will consume
+        auto tile_wait = [&]() -> const cplx * {
+            const int slot = tile_n % RING;
+            mb_wait(&full[slot], (tile_n / RING) & 1);
+            return ring + (size_t)slot * TILE + t;
+        };
+        auto tile_done = [&]() { mb_arrive(&empty[tile_n % RING]); tile_n++; };
+
+        if (live) {
+            if (!a.step_mode) {
+                uint32_t z[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) z[i] = 0u;
+                const uint64_t gv = t == 0 ? (uint64_t)1 << (64 - (row + 1) * a.logB_lev) : 0;   // bootstrapping.jl:402-408
+#pragma unroll
+                for (int c = 0; c < 128; c += 16) {            // tcgen05.st is warp-collective: same instruction on every lane
+                    z[0] = c == 0 ? (uint32_t)gv : 0u;
+                    z[1] = c == 0 ? (uint32_t)(gv >> 32) : 0u;
+                    tm_st16(tm + c, z);
+                }
+            } else {
+                const uint64_t *src = a.acc_io + up * 2 * N;
+#pragma unroll
+                for (int pz = 0; pz < 2; pz++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t v[16];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int ci = 8 * c + i;
+                            const uint64_t w = src[pz * N + t + 64 * (ci & 15) + (ci >> 4) * H];
+                            v[2 * i] = (uint32_t)w; v[2 * i + 1] = (uint32_t)(w >> 32);
+                        }
+                        tm_st16(tm + pz * 64 + 16 * c, v);
+                    }
+            }
+            tm_wait_st();
+        }
+        const int logB = a.logB;
+        const int bit = 64 - l * logB;
+        uint64_t cadd = (uint64_t)1 << (bit - 1);
+        for (int j = 0; j < l; j++) cadd += (uint64_t)1 << (bit + j * logB + logB - 1);
+        const uint32_t mask = (1u << logB) - 1;
+        const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));
+        const uint32_t *at_src = a.step_mode ? a.tilde + up * ELL : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
+        const int brv6t = (int)(__brev((unsigned)t) >> 26);
+
+        for (int step = 0; step < nsteps; step++) {
+            uint32_t atv[ELL];
+            bool any = false;
+#pragma unroll
+            for (int b = 0; b < ELL; b++) { atv[b] = live ? at_src[(a.step_mode ? 0 : step * ELL) + b] : 0u; any |= atv[b] > 0; }
+            if (!any) {                                        // :413 / dead unit: keep the ring moving, compute nothing
+                for (int i = 0; i < 2 * l * ELL * 2; i++) { tile_wait(); tile_done(); }
+                continue;
+            }
+            cplx m1v[ELL];
+#pragma unroll
+            for (int b = 0; b < ELL; b++) m1v[b] = __ldg(&a.tb.emono[((4 * brv6t + 1) * atv[b]) & 4095]);
+
+            for (int dg = 0; dg < 2 * l; dg++) {
+                const uint32_t src = tm + (dg < l ? TM_ACC_B : TM_ACC_A);
+                const int sh = bit + (l - 1 - (dg < l ? dg : dg - l)) * logB;
+                cplx x[16];
+                {
+                    uint32_t lo[32], hi[32];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t v[16];
+                        tm_ld16(src + 16 * c, v);
+                        tm_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { lo[8 * c + i] = v[2 * i]; hi[8 * c + i] = v[2 * i + 1]; }
+                    }
+#pragma unroll
+                    for (int m = 0; m < 16; m++) {
+                        const uint64_t v0 = (((uint64_t)hi[m] << 32) | lo[m]) + cadd, v1 = (((uint64_t)hi[m + 16] << 32) | lo[m + 16]) + cadd;
+                        const uint32_t f0 = (uint32_t)(v0 >> sh) & mask, f1 = (uint32_t)(v1 >> sh) & mask;
+                        x[m] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
+                    }
+                }
+                fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+                cplx kcb[16], kca[16];
+                if (ELL == 1) {
+                    const cplx *kb = tile_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; e++) kcb[e] = kb[e * UT];
+                    tile_done();
+                    const cplx *ka = tile_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; e++) kca[e] = ka[e * UT];
+                    tile_done();
+                } else {
+                    // block: fold the monomials of the block's key bits into the keys (see k_phase1)
+#pragma unroll
+                    for (int e = 0; e < 16; e++) kcb[e] = kca[e] = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int b = 0; b < ELL; b++) {
+                        const cplx *kb = tile_wait();
+                        const int slot_b = tile_n % RING;
+                        tile_n++;                                   // hold the .b tile while the .a tile is awaited
+                        const cplx *ka = tile_wait();
+                        if (atv[b] != 0) {
+#pragma unroll
+                            for (int e = 0; e < 16; e++) {
+                                const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
+                                cplx mo = cmul_f(m1v[b], c_e16[(atv[b] * b4) & 15]);
+                                mo.x -= 1.0 / H;
+                                kcb[e] = cmac_f(kcb[e], mo, kb[e * UT]);
+                                kca[e] = cmac_f(kca[e], mo, ka[e * UT]);
+                            }
+                        }
+                        mb_arrive(&empty[slot_b]);
+                        tile_done();
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    cplx zb[4], za[4];
+                    if (dg == 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { zb[i] = cmul_f(x[4 * c + i], kcb[4 * c + i]); za[i] = cmul_f(x[4 * c + i], kca[4 * c + i]); }
+                    } else {
+                        tm_ld_c4(tm + TM_TACC_B + 16 * c, zb);
+                        tm_ld_c4(tm + TM_TACC_A + 16 * c, za);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { zb[i] = cmac_f(zb[i], x[4 * c + i], kcb[4 * c + i]); za[i] = cmac_f(za[i], x[4 * c + i], kca[4 * c + i]); }
+                    }
+                    tm_st_c4(tm + TM_TACC_B + 16 * c, zb);
+                    tm_st_c4(tm + TM_TACC_A + 16 * c, za);
+                }
+                tm_wait_st();
+            }
+            // both outputs: (x (X^a - 1)/H for ELL == 1) -> inverse transform -> round -> acc +=
+#pragma unroll 1
+            for (int pz = 0; pz < 2; pz++) {
+                cplx y[16];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    cplx z[4];
+                    tm_ld_c4(tm + (pz == 0 ? TM_TACC_B : TM_TACC_A) + 16 * c, z);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) y[4 * c + i] = z[i];
+                }
+                if (ELL == 1) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
+                        cplx mo = cmul_f(m1v[0], c_e16[(atv[0] * b4) & 15]);
+                        mo.x -= 1.0 / H;
+                        y[e] = cmul_f(mo, y[e]);
+                    }
+                }
+                fft_inv2(y, xa, xc, tw2, tw8, tw9e, t, unit_l);
+                const uint32_t dst = tm + (pz == 0 ? TM_ACC_B : TM_ACC_A);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t v[16];
+                    tm_ld16(dst + 16 * c, v);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int ci = 8 * c + i, m = ci & 15;
+                        const uint64_t add = d2torus(ci < 16 ? y[m].x : -y[m].y);
+                        const uint64_t w = (((uint64_t)v[2 * i + 1] << 32) | v[2 * i]) + add;
+                        v[2 * i] = (uint32_t)w; v[2 * i + 1] = (uint32_t)(w >> 32);
+                    }
+                    tm_st16(dst + 16 * c, v);
+                }
+                tm_wait_st();
+            }
+        }
+
+        if (live) {
+            if (!a.step_mode) {            // fftto!(tacc, acc): bootstrapping.jl:441
+                cplx *out = a.lev_out + unit_out * 2 * H;
+#pragma unroll 1
+                for (int pz = 0; pz < 2; pz++) {
+                    cplx x[16];
+                    uint32_t lo[32], hi[32];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t v[16];
+                        tm_ld16(tm + pz * 64 + 16 * c, v);
+                        tm_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { lo[8 * c + i] = v[2 * i]; hi[8 * c + i] = v[2 * i + 1]; }
+                    }
+#pragma unroll
+                    for (int m = 0; m < 16; m++) {
+                        const uint64_t v0 = ((uint64_t)hi[m] << 32) | lo[m], v1 = ((uint64_t)hi[m + 16] << 32) | lo[m + 16];
+                        x[m] = make_double2(__ll2double_rn((long long)v0), __ll2double_rn((long long)((uint64_t)0 - v1)));
+                    }
+                    fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+#pragma unroll
+                    for (int e = 0; e < 16; e++) out[(size_t)pz * H + 16 * t + e] = x[e];
+                }
+            } else {
+                uint64_t *dst = a.acc_io + up * 2 * N;
+#pragma unroll
+                for (int pz = 0; pz < 2; pz++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t v[16];
+                        tm_ld16(tm + pz * 64 + 16 * c, v);
+                        tm_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int ci = 8 * c + i;
+                            dst[pz * N + t + 64 * (ci & 15) + (ci >> 4) * H] = ((uint64_t)v[2 * i + 1] << 32) | v[2 * i];
+                        }
+                    }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tm_base_s));
+}
+
 // reference slot order [poly][16t + e] -> thread order [poly][e][t]
 __global__ void k_permute_brk(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -824,10 +1122,10 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
     FCK(cudaMemcpy(f.d_brk, f.brk.data(), sizeof(cplx *) * f.brk.size(), cudaMemcpyHostToDevice));
     FCK(cudaFuncSetAttribute(k_phase1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     FCK(cudaFuncSetAttribute(k_phase1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    FCK(cudaFuncSetAttribute(k_phase1_tm<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
-    FCK(cudaFuncSetAttribute(k_phase1_tm<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
-    FCK(cudaFuncSetAttribute(k_phase1_tm<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
-    FCK(cudaFuncSetAttribute(k_phase1_tm<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
+    FCK(cudaFuncSetAttribute(k_phase1_tm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
+    FCK(cudaFuncSetAttribute(k_phase1_tm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
+    FCK(cudaFuncSetAttribute(k_phase1_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TMA));
+    FCK(cudaFuncSetAttribute(k_phase1_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TMA));
     f.built = true;
     return 0;
 }
@@ -840,19 +1138,36 @@ static inline int fast_launch(FastKeys &f, const mktfhe_params &p, fast::Args a,
     a.R = 1 + (p.k - 1) * p.l_lev; a.lwe_words = (int)mktfhe_lwe_words(&p);
     const unsigned grid = (unsigned)((a.units + U - 1) / U);
     a.d = p.d;
-    static const bool use_tmem = []() { const char *e = getenv("MKTFHE_FAST_KERNEL"); return !(e && std::string(e) == "smem"); }();
-    if (use_tmem) {
-        static const int pf = []() { const char *e = getenv("MKTFHE_FAST_PF"); return e ? atoi(e) : 0; }();
-        if (p.scheme == MKTFHE_KMS_BLOCK) k_phase1_tm<3, 0><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
-        else if (pf == 1) k_phase1_tm<1, 1><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
-        else if (pf == 2) k_phase1_tm<1, 2><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
-        else k_phase1_tm<1, 0><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
+    static const std::string variant = []() { const char *e = getenv("MKTFHE_FAST_KERNEL"); return std::string(e ? e : "tma"); }();
+    if (variant == "tma") {
+        // CTAs are grouped by party (one key stream per CTA): ceil(gates/U) for party 0 plus ceil(gates*l_lev/U) per other party
+        size_t ctas;
+        if (a.step_mode) ctas = (a.units + U - 1) / U;
+        else {
+            const size_t gates = a.units / a.R;
+            ctas = (gates + U - 1) / U + (size_t)(p.k - 1) * ((gates * p.l_lev + U - 1) / U);
+        }
+        if (p.scheme == MKTFHE_KMS_BLOCK) k_phase1_tma<3><<<(unsigned)ctas, CTA_TMA, SMEM_BYTES_TMA, stream>>>(a);
+        else k_phase1_tma<1><<<(unsigned)ctas, CTA_TMA, SMEM_BYTES_TMA, stream>>>(a);
+    } else if (variant == "tmem") {
+        if (p.scheme == MKTFHE_KMS_BLOCK) k_phase1_tm<3><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
+        else k_phase1_tm<1><<<grid, CTA, SMEM_BYTES_TM, stream>>>(a);
     } else {
         if (p.scheme == MKTFHE_KMS_BLOCK) k_phase1<3><<<grid, CTA, SMEM_BYTES, stream>>>(a);
         else k_phase1<1><<<grid, CTA, SMEM_BYTES, stream>>>(a);
     }
     if (launches) (*launches)++;
-    FCK(cudaGetLastError());
+    {
+        cudaError_t e_ = cudaGetLastError();
+        if (e_ != cudaSuccess) {
+            cudaFuncAttributes fa{};
+            cudaFuncGetAttributes(&fa, k_phase1_tma<1>);
+            err = std::string("phase-1 launch (") + variant + "): " + cudaGetErrorString(e_) + " [regs " + std::to_string(fa.numRegs) +
+                  ", static smem " + std::to_string(fa.sharedSizeBytes) + ", max dyn smem " + std::to_string(fa.maxDynamicSharedSizeBytes) +
+                  ", max threads " + std::to_string(fa.maxThreadsPerBlock) + "]";
+            return MKTFHE_ERR_CUDA_;
+        }
+    }
     return 0;
 }
 
