@@ -403,12 +403,20 @@ __device__ __forceinline__ void tm_ld16(uint32_t addr, uint32_t (&v)[16]) {
                  : "r"(addr) : "memory");
 }
 __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld is asynchronous: its destination registers are only valid after tcgen05.wait::ld.  The compiler sees no
+// data dependency between the wait and those registers, so every consumer first passes them through this empty
+// volatile asm (volatile asms keep their order), which pins all later uses behind the wait.
+__device__ __forceinline__ void tm_pin16(uint32_t (&v)[16]) {
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                      "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]) :: "memory");
+}
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // 4 complex doubles <-> 16 TMEM columns
 __device__ __forceinline__ void tm_ld_c4(uint32_t addr, cplx (&z)[4]) {
     uint32_t v[16];
     tm_ld16(addr, v);
     tm_wait_ld();
+    tm_pin16(v);
 #pragma unroll
     for (int i = 0; i < 4; i++) z[i] = make_double2(__hiloint2double((int)v[4 * i + 1], (int)v[4 * i]), __hiloint2double((int)v[4 * i + 3], (int)v[4 * i + 2]));
 }
@@ -556,6 +564,7 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
                         uint32_t v[16];
                         tm_ld16(src + 16 * c, v);
                         tm_wait_ld();
+                        tm_pin16(v);
 #pragma unroll
                         for (int i = 0; i < 8; i++) { lo[8 * c + i] = v[2 * i]; hi[8 * c + i] = v[2 * i + 1]; }
                     }
@@ -658,6 +667,7 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
                     uint32_t v[16];
                     tm_ld16(dst + 16 * c, v);
                     tm_wait_ld();
+                    tm_pin16(v);
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int ci = 8 * c + i, m = ci & 15;
@@ -682,6 +692,7 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
                     uint32_t v[16];
                     tm_ld16(tm + pz * 64 + 16 * c, v);
                     tm_wait_ld();
+                    tm_pin16(v);
 #pragma unroll
                     for (int i = 0; i < 8; i++) { lo[8 * c + i] = v[2 * i]; hi[8 * c + i] = v[2 * i + 1]; }
                 }
@@ -703,6 +714,7 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
                     uint32_t v[16];
                     tm_ld16(tm + pz * 64 + 16 * c, v);
                     tm_wait_ld();
+                    tm_pin16(v);
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int ci = 8 * c + i;
@@ -881,6 +893,7 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                         uint32_t v[16];
                         tm_ld16(src + 16 * c, v);
                         tm_wait_ld();
+                        tm_pin16(v);
 #pragma unroll
                         for (int i = 0; i < 8; i++) { lo[8 * c + i] = v[2 * i]; hi[8 * c + i] = v[2 * i + 1]; }
                     }
@@ -970,6 +983,7 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                     uint32_t v[16];
                     tm_ld16(dst + 16 * c, v);
                     tm_wait_ld();
+                    tm_pin16(v);
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int ci = 8 * c + i, m = ci & 15;
@@ -995,6 +1009,7 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                         uint32_t v[16];
                         tm_ld16(tm + pz * 64 + 16 * c, v);
                         tm_wait_ld();
+                        tm_pin16(v);
 #pragma unroll
                         for (int i = 0; i < 8; i++) { lo[8 * c + i] = v[2 * i]; hi[8 * c + i] = v[2 * i + 1]; }
                     }
@@ -1016,6 +1031,7 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                         uint32_t v[16];
                         tm_ld16(tm + pz * 64 + 16 * c, v);
                         tm_wait_ld();
+                        tm_pin16(v);
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
                             const int ci = 8 * c + i;
