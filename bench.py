@@ -33,7 +33,7 @@ GATE_SEED = 0x47415445
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default batch, from `ncu` captures committed under
 # profiles/ (r1_traffic_kms2.csv); null for workloads not captured.
-TRAFFIC = {"kms2": {"phase1": 46152832256 + 480913152, "keyswitch": 507604480 + 26476544, "phase2": 404378368 + 421909248}}
+TRAFFIC = {"kms2": {"phase1": 5345095424 + 415138048, "keyswitch": 505005056 + 26237440, "phase2": 405425152 + 423150080}}
 
 WORKLOADS = {  # name -> (parameter set, default per-GPU batch)
     "kms2": ("KMS2party", 4096),
@@ -347,9 +347,9 @@ def main():
         dom_ms = stage_ms[dom]
         peak = scheme.dfma_peak_tflops()
         ach = alg["phase1"] * batch / (dom_ms * 1e-3) / 1e3 if dom_ms > 0 else 0.0
-        line["roofline"] = {"bound": "fp64", "kernel": "phase 1 blind rotation (FFT + RGSW MAC)", "achieved": ach, "peak": peak,
+        line["roofline"] = {"bound": "fp64", "kernel": "blind rotation (FP64 transforms + pointwise MAC): fast::k_phase1_tma / k_rgsw_tm / k_ccs_fast", "achieved": ach, "peak": peak,
                             "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": TRAFFIC.get(args.workload, {}).get("phase1"),
-                            "peak_source": "measured in this run: register-only DFMA loop (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
+                            "peak_source": "measured in this run: register-only DFMA loop, 16 chains x 16 warps/SM (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
                             "algorithmic_gflop_per_gate": alg, "kernel_ms_per_launch": dom_ms}
         try:
             hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
