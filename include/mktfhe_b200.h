@@ -99,6 +99,21 @@ int mktfhe_sync(mktfhe_ctx *ctx);
 /* The CUDA stream (cudaStream_t) all work of this context is launched on, for event timing. */
 void *mktfhe_stream(mktfhe_ctx *ctx);
 
+/* ---- gate circuits (the caller side of the path) ----------------------------- */
+/* The reference evaluates a circuit one gate call at a time (test/KMS.jl:28-36 chains NAND ... NOR calls); here the
+ * circuit's wires live in a device-resident table of LWE records owned by the context, and one call evaluates one
+ * LEVEL of independent gates:  for g < batch:  wires[dst[g]] = bootstrap(op[g](wires[src1[g]], wires[src2[g]])).
+ *   ops[g]: MKTFHE_NAND .. MKTFHE_NOR (gate.jl:1-52), -1 = bootstrapping! of src1 alone, MKTFHE_NOT = NOT! of src1
+ *   (negation only, no bootstrap, gate.jl:55-58).  ops / src1 / src2 / dst are HOST arrays of `batch` entries.
+ * A dst wire must not also be a source of the same call (levels of a circuit in SSA form satisfy this).
+ * Synchronous: the level has completed when the call returns. */
+int mktfhe_wires_resize(mktfhe_ctx *ctx, size_t nwires);     /* (re)allocates the table, zero-filled; 0 frees it */
+/* Copies `count` LWE records ([count][1 + n*k] uint32; host or device pointer) into / out of wires first .. first+count-1. */
+int mktfhe_wires_write(mktfhe_ctx *ctx, size_t first, size_t count, const uint32_t *cts);
+int mktfhe_wires_read(mktfhe_ctx *ctx, size_t first, size_t count, uint32_t *cts);
+int mktfhe_gate_level(mktfhe_ctx *ctx, const int32_t *ops, const int32_t *src1, const int32_t *src2,
+                      const int32_t *dst, size_t batch);
+
 /* ---- parity / debug hooks (host buffers) ------------------------------------------------------- */
 /* gate.jl linear part only. */
 int mktfhe_gate_linear_batch(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2,

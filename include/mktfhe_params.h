@@ -21,7 +21,8 @@ extern "C" {
 
 enum mktfhe_scheme { MKTFHE_CGGI = 0, MKTFHE_LMSS = 1, MKTFHE_CCS = 2, MKTFHE_KMS = 3, MKTFHE_KMS_BLOCK = 4 };
 /* gate opcodes: /root/reference/src/tfhe/gate.jl:1-52 */
-enum mktfhe_gate { MKTFHE_NAND = 0, MKTFHE_AND = 1, MKTFHE_OR = 2, MKTFHE_XOR = 3, MKTFHE_XNOR = 4, MKTFHE_NOR = 5 };
+enum mktfhe_gate { MKTFHE_NAND = 0, MKTFHE_AND = 1, MKTFHE_OR = 2, MKTFHE_XOR = 3, MKTFHE_XNOR = 4, MKTFHE_NOR = 5,
+                   MKTFHE_NOT = 6 /* circuit levels only: negation, no bootstrap (gate.jl:55-58) */ };
 
 typedef struct mktfhe_params {
     int32_t scheme;            /* enum mktfhe_scheme */

@@ -17,6 +17,7 @@ EXPORTS = [
     "mktfhe_gate_linear_batch", "mktfhe_modswitch_batch", "mktfhe_blindrotate_batch", "mktfhe_phase1_batch",
     "mktfhe_keyswitch_batch", "mktfhe_cmux_step_batch", "mktfhe_block_step_batch", "mktfhe_fft_batch", "mktfhe_ifft_batch",
     "mktfhe_decomp_batch", "mktfhe_last_stage_ms", "mktfhe_measure_dfma_peak",
+    "mktfhe_wires_resize", "mktfhe_wires_write", "mktfhe_wires_read", "mktfhe_gate_level",
 ]
 
 
@@ -46,6 +47,10 @@ def lib() -> ctypes.CDLL:
     L.mktfhe_sync.argtypes = [vp]
     L.mktfhe_stream.argtypes = [vp]
     L.mktfhe_stream.restype = vp
+    L.mktfhe_wires_resize.argtypes = [vp, sz]
+    L.mktfhe_wires_write.argtypes = [vp, sz, sz, vp]
+    L.mktfhe_wires_read.argtypes = [vp, sz, sz, vp]
+    L.mktfhe_gate_level.argtypes = [vp, vp, vp, vp, vp, sz]
     L.mktfhe_gate_linear_batch.argtypes = [vp, i32, vp, vp, vp, sz]
     L.mktfhe_modswitch_batch.argtypes = [vp, vp, vp, sz]
     L.mktfhe_blindrotate_batch.argtypes = [vp, vp, vp, sz]

@@ -44,6 +44,10 @@ struct mktfhe_ctx {
     uint32_t *w_in1 = nullptr, *w_in2 = nullptr, *w_out = nullptr, *w_lin = nullptr, *w_tilde = nullptr, *w_v = nullptr;
     void *w_acc = nullptr;
     cplx *w_lev = nullptr, *w_tx = nullptr, *w_ty = nullptr;
+    // circuit wire table (mktfhe_wires_*): nwires LWE records, plus per-level index scratch for `idx_cap` gates
+    uint32_t *wires = nullptr;
+    size_t nwires = 0, idx_cap = 0;
+    int32_t *w_idx = nullptr;                        // [4][idx_cap]: ops, src1, src2, dst
     // measurement
     std::vector<StageEvents> events;
     size_t events_used = 0;
@@ -82,6 +86,11 @@ void free_workspace(mktfhe_ctx *c) {
     dfree(c->w_in1); dfree(c->w_in2); dfree(c->w_out); dfree(c->w_lin); dfree(c->w_tilde); dfree(c->w_v);
     dfree(c->w_acc); dfree(c->w_lev); dfree(c->w_tx); dfree(c->w_ty);
     c->cap = 0;
+}
+
+void free_wires(mktfhe_ctx *c) {
+    dfree(c->wires); dfree(c->w_idx);
+    c->nwires = c->idx_cap = 0;
 }
 
 int ensure_workspace(mktfhe_ctx *ctx, size_t gates) {
@@ -135,10 +144,12 @@ int run_rgsw(mktfhe_ctx *ctx, RgswArgs a, size_t units) {
     return blk ? launch_rgsw<uint32_t, 512, 3>(ctx, a, units) : launch_rgsw<uint32_t, 512, 1>(ctx, a, units);
 }
 
-int run_prep(mktfhe_ctx *ctx, int op, const uint32_t *in1, const uint32_t *in2, uint32_t *lin, uint32_t *tilde, size_t gates) {
+int run_prep(mktfhe_ctx *ctx, int op, const uint32_t *in1, const uint32_t *in2, uint32_t *lin, uint32_t *tilde, size_t gates,
+             const int32_t *ops = nullptr, const int32_t *idx1 = nullptr, const int32_t *idx2 = nullptr) {
     const size_t total = gates * mktfhe_lwe_words(&ctx->p);
     int logN = 0; while ((1 << logN) < ctx->N) logN++;
-    k_gate_prep<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in1, in2, lin, tilde, op, (int)mktfhe_lwe_words(&ctx->p), total, 32 - logN - 1);
+    k_gate_prep<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in1, in2, lin, tilde, op, (int)mktfhe_lwe_words(&ctx->p), total, 32 - logN - 1,
+                                                                         ops, idx1, idx2);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -394,6 +405,7 @@ void mktfhe_ctx_destroy(mktfhe_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     free_workspace(ctx);
+    free_wires(ctx);
     fast_free(ctx->fast);
     fast32_free(ctx->fast32);
     fastccs_free(ctx->fastccs);
@@ -498,12 +510,13 @@ int mktfhe_sync(mktfhe_ctx *ctx) {
 
 void *mktfhe_stream(mktfhe_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
-static int run_pipeline(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2, uint32_t *out, size_t g) {
+static int run_pipeline(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2, uint32_t *out, size_t g,
+                        const int32_t *ops = nullptr, const int32_t *idx1 = nullptr, const int32_t *idx2 = nullptr) {
     int rc;
     StageEvents *ev = next_events(ctx);
     if (!ev) return fail(ctx, MKTFHE_ERR_CUDA, "cudaEventCreate failed");
     cudaEventRecord(ev->e[0], ctx->stream);
-    if ((rc = run_prep(ctx, gate_op, in1, in2, nullptr, ctx->w_tilde, g))) return rc;
+    if ((rc = run_prep(ctx, gate_op, in1, in2, nullptr, ctx->w_tilde, g, ops, idx1, idx2))) return rc;
     cudaEventRecord(ev->e[1], ctx->stream);
     if ((rc = run_blindrotate(ctx, ctx->w_tilde, g, ev))) return rc;
     cudaEventRecord(ev->e[3], ctx->stream);
@@ -567,6 +580,104 @@ int mktfhe_last_stage_ms(mktfhe_ctx *ctx, float *ms_out, int *launches_out) {
             ms_out[s] += ms;
         }
     if (launches_out) *launches_out = ctx->launches;
+    return 0;
+}
+
+// ---- gate circuits over a device-resident wire table ------------------------------------------------
+
+int mktfhe_wires_resize(mktfhe_ctx *ctx, size_t nwires) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx->wires);
+    ctx->nwires = 0;
+    if (nwires == 0) return 0;
+    if (nwires > (size_t)INT32_MAX) return fail(ctx, MKTFHE_ERR_ARG, "wire count above 2^31 - 1");
+    const size_t bytes = nwires * mktfhe_lwe_words(&ctx->p) * 4;
+    CK(cudaMalloc(&ctx->wires, bytes));
+    CK(cudaMemsetAsync(ctx->wires, 0, bytes, ctx->stream));
+    ctx->nwires = nwires;
+    return 0;
+}
+
+int mktfhe_wires_write(mktfhe_ctx *ctx, size_t first, size_t count, const uint32_t *cts) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (first + count > ctx->nwires || first + count < first) return fail(ctx, MKTFHE_ERR_ARG, "wire range outside the table");
+    if (count == 0) return 0;
+    if (!cts) return fail(ctx, MKTFHE_ERR_ARG, "null ciphertext pointer");
+    const size_t lw = mktfhe_lwe_words(&ctx->p);
+    CK(cudaMemcpyAsync(ctx->wires + first * lw, cts, count * lw * 4, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mktfhe_wires_read(mktfhe_ctx *ctx, size_t first, size_t count, uint32_t *cts) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (first + count > ctx->nwires || first + count < first) return fail(ctx, MKTFHE_ERR_ARG, "wire range outside the table");
+    if (count == 0) return 0;
+    if (!cts) return fail(ctx, MKTFHE_ERR_ARG, "null ciphertext pointer");
+    const size_t lw = mktfhe_lwe_words(&ctx->p);
+    CK(cudaMemcpyAsync(cts, ctx->wires + first * lw, count * lw * 4, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mktfhe_gate_level(mktfhe_ctx *ctx, const int32_t *ops, const int32_t *src1, const int32_t *src2, const int32_t *dst, size_t batch) {
+    int rc;
+    if ((rc = check_ready(ctx))) return rc;
+    if (batch == 0) return 0;
+    if (!ops || !src1 || !src2 || !dst) return fail(ctx, MKTFHE_ERR_ARG, "null index array");
+    if (!ctx->wires) return fail(ctx, MKTFHE_ERR_STATE, "no wire table: call mktfhe_wires_resize first");
+    // split into bootstrapped gates and NOTs; validate every index before touching the device
+    std::vector<int32_t> b_ops, b_s1, b_s2, b_dst, n_src, n_dst;
+    const int64_t nw = (int64_t)ctx->nwires;
+    for (size_t g = 0; g < batch; g++) {
+        const int op = ops[g];
+        if (op < -1 || op > MKTFHE_NOT) return fail(ctx, MKTFHE_ERR_ARG, "bad gate opcode at gate " + std::to_string(g));
+        const bool two = op >= 0 && op <= MKTFHE_NOR;
+        if (src1[g] < 0 || src1[g] >= nw || dst[g] < 0 || dst[g] >= nw || (two && (src2[g] < 0 || src2[g] >= nw)))
+            return fail(ctx, MKTFHE_ERR_ARG, "wire index outside the table at gate " + std::to_string(g));
+        if (op == MKTFHE_NOT) { n_src.push_back(src1[g]); n_dst.push_back(dst[g]); }
+        else { b_ops.push_back(op); b_s1.push_back(src1[g]); b_s2.push_back(two ? src2[g] : 0); b_dst.push_back(dst[g]); }
+    }
+    const size_t lw = mktfhe_lwe_words(&ctx->p), nb = b_ops.size(), nn = n_src.size();
+    const size_t need = nb > nn ? nb : nn;
+    if (need > ctx->idx_cap) {
+        dfree(ctx->w_idx);
+        ctx->idx_cap = 0;
+        CK(cudaMalloc(&ctx->w_idx, 4 * need * sizeof(int32_t)));
+        ctx->idx_cap = need;
+    }
+    int32_t *d_ops = ctx->w_idx, *d_s1 = d_ops + ctx->idx_cap, *d_s2 = d_s1 + ctx->idx_cap, *d_dst = d_s2 + ctx->idx_cap;
+    ctx->events_used = 0; ctx->launches = 0;
+    if (nb) {
+        const size_t chunk = chunk_gates(ctx, nb);
+        if ((rc = ensure_workspace(ctx, chunk))) return rc;
+        CK(cudaMemcpyAsync(d_ops, b_ops.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_s1, b_s1.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_s2, b_s2.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_dst, b_dst.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+        for (size_t g0 = 0; g0 < nb; g0 += chunk) {
+            const size_t g = nb - g0 < chunk ? nb - g0 : chunk;
+            if ((rc = run_pipeline(ctx, 0, ctx->wires, ctx->wires, ctx->w_out, g, d_ops + g0, d_s1 + g0, d_s2 + g0))) return rc;
+            const size_t total = g * lw;
+            k_wire_scatter<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->w_out, ctx->wires, nullptr, d_dst + g0, (int)lw, total, 0);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        CK(cudaStreamSynchronize(ctx->stream));            // the host index vectors die with this call
+    }
+    if (nn) {
+        CK(cudaMemcpyAsync(d_s1, n_src.data(), nn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_dst, n_dst.data(), nn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        const size_t total = nn * lw;
+        k_wire_scatter<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(nullptr, ctx->wires, d_s1, d_dst, (int)lw, total, 1);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     return 0;
 }
 

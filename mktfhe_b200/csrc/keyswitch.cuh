@@ -8,15 +8,22 @@
 #include "common.cuh"
 
 // lin = gate linear combination (or copy when op < 0); tilde = divbits(lin, 32 - log2(N) - 1).
+// Circuit levels pass per-gate opcodes (`ops`) and gather the operands from a wire table (`idx1`, `idx2`: row
+// indices into in1 / in2); all three are null for a plain batch.
 __global__ void k_gate_prep(const uint32_t *in1, const uint32_t *in2, uint32_t *lin, uint32_t *tilde,
-                            int op, int lwe_words, size_t total, int shift) {
+                            int op, int lwe_words, size_t total, int shift,
+                            const int32_t *ops = nullptr, const int32_t *idx1 = nullptr, const int32_t *idx2 = nullptr) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const bool is_b = (i % lwe_words) == 0;
+    const size_t g = i / lwe_words, w = i % lwe_words;
+    const bool is_b = w == 0;
+    if (ops) op = ops[g];
+    const size_t i1 = idx1 ? (size_t)idx1[g] * lwe_words + w : i;
     uint32_t v;
-    if (op < 0) v = in1[i];
+    if (op < 0) v = in1[i1];
     else {
-        const uint32_t s = in1[i] + in2[i];
+        const size_t i2 = idx2 ? (size_t)idx2[g] * lwe_words + w : i;
+        const uint32_t s = in1[i1] + in2[i2];
         uint32_t cst;
         switch (op) {                                    // Julia: `T(c) << 29 - x - y` = (c << 29) - x - y
         case 0:  cst = 1u << 29; v = 0u - s; break;      // NAND  gate.jl:2-4
@@ -30,6 +37,17 @@ __global__ void k_gate_prep(const uint32_t *in1, const uint32_t *in2, uint32_t *
     }
     if (lin) lin[i] = v;
     if (tilde) tilde[i] = divbits<uint32_t>(v, shift);
+}
+
+// Wire-table plumbing of a circuit level: rows of `src` (one per gate) go to wires[dst[g]]; with negate, rows are
+// gathered from wires[from[g]] and negated on the way (NOT!, gate.jl:55-58: no bootstrap).
+__global__ void k_wire_scatter(const uint32_t *src, uint32_t *wires, const int32_t *from, const int32_t *dst,
+                               int lwe_words, size_t total, int negate) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t g = i / lwe_words, w = i % lwe_words;
+    const uint32_t v = negate ? 0u - wires[(size_t)from[g] * lwe_words + w] : src[i];
+    wires[(size_t)dst[g] * lwe_words + w] = v;
 }
 
 struct KsArgs {

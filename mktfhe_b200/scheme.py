@@ -14,6 +14,7 @@ from .params import Params
 
 MODE_STRICT, MODE_FAST = 0, 1
 NAND_OP, AND_OP, OR_OP, XOR_OP, XNOR_OP, NOR_OP = range(6)
+NOT_OP, BOOTSTRAP_OP = 6, -1                     # circuit levels only (include/mktfhe_params.h)
 STAGES = ("prep", "phase1", "phase2", "keyswitch")
 
 
@@ -116,6 +117,27 @@ class Scheme:
     @property
     def stream(self) -> int:
         return _lib.lib().mktfhe_stream(self._h) or 0
+
+    # -- circuits: device-resident wire table (include/mktfhe_b200.h, "gate circuits") -------------------
+    def wires_resize(self, nwires: int):
+        self._ck(_lib.lib().mktfhe_wires_resize(self._h, int(nwires)), "mktfhe_wires_resize")
+
+    def wires_write(self, first: int, cts):
+        cts, _ = self._batchify(cts)
+        self._ck(_lib.lib().mktfhe_wires_write(self._h, int(first), cts.shape[0], _ptr(cts)), "mktfhe_wires_write")
+
+    def wires_read(self, first: int, count: int):
+        out = np.empty((int(count), self.params.lwe_words), dtype=np.uint32)
+        self._ck(_lib.lib().mktfhe_wires_read(self._h, int(first), int(count), _ptr(out)), "mktfhe_wires_read")
+        return out
+
+    def gate_level(self, ops, src1, src2, dst):
+        """One level of independent gates over the wire table: wires[dst] = bootstrap(op(wires[src1], wires[src2]))."""
+        arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (ops, src1, src2, dst)]
+        n = arrs[0].shape[0]
+        if any(a.shape != (n,) for a in arrs):
+            raise ValueError("ops, src1, src2 and dst must be 1-D arrays of one length")
+        self._ck(_lib.lib().mktfhe_gate_level(self._h, *[_ptr(a) for a in arrs], n), "mktfhe_gate_level")
 
     # -- parity hooks -----------------------------------------------------------------------------
     @property
