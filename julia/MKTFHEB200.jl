@@ -136,4 +136,27 @@ function bootstrapping!(c::LWE{UInt32}, s::GPUScheme)
     c
 end
 
+# ---- circuits: one call per level of independent gates over a device-resident wire table (include/mktfhe_b200.h) ----
+# ops: 0..5 = NAND..NOR, -1 = bootstrapping! of src1, 6 = NOT! (no bootstrap).  Wire indices are 0-based rows of the table.
+wires_resize(s::GPUScheme, n::Integer) =
+    check(ccall((:mktfhe_wires_resize, LIB), Cint, (Ptr{Cvoid}, Csize_t), s.h, n), s.h)
+
+function wires_write(s::GPUScheme, first::Integer, cs::Vector{LWE{UInt32}})
+    buf = pack(cs)
+    GC.@preserve buf check(ccall((:mktfhe_wires_write, LIB), Cint,
+        (Ptr{Cvoid}, Csize_t, Csize_t, Ptr{UInt32}), s.h, first, length(cs), buf), s.h)
+end
+
+function wires_read(s::GPUScheme, first::Integer, count::Integer)
+    buf = Vector{UInt32}(undef, count * s.words)
+    GC.@preserve buf check(ccall((:mktfhe_wires_read, LIB), Cint,
+        (Ptr{Cvoid}, Csize_t, Csize_t, Ptr{UInt32}), s.h, first, count, buf), s.h)
+    unpack(buf, s.words)
+end
+
+function gate_level(s::GPUScheme, ops::Vector{Int32}, src1::Vector{Int32}, src2::Vector{Int32}, dst::Vector{Int32})
+    GC.@preserve ops src1 src2 dst check(ccall((:mktfhe_gate_level, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Csize_t), s.h, ops, src1, src2, dst, length(ops)), s.h)
+end
+
 end # module
