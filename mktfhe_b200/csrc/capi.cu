@@ -1,6 +1,8 @@
 // capi.cu -- C-ABI of include/mktfhe_b200.h: context, key upload, batch pipeline, parity hooks.
 #include "../../include/mktfhe_b200.h"
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -24,7 +26,7 @@ struct StageEvents { cudaEvent_t e[MKTFHE_STAGE_COUNT + 1]; };
 
 struct mktfhe_ctx {
     mktfhe_params p;
-    int device = 0, mode = MKTFHE_MODE_STRICT;
+    int device = 0, mode = MKTFHE_MODE_STRICT, sms = 148;
     int N = 0, H = 0, bits = 32, R = 1, nparties = 1;
     bool mk = false, kms = false, block = false;
     cudaStream_t stream = nullptr;
@@ -199,21 +201,33 @@ int run_keyswitch(mktfhe_ctx *ctx, const void *acc, uint32_t *out, size_t gates)
     a.acc = acc; a.ksk = ctx->d_ksk; a.out = out;
     a.N = ctx->N; a.n = p.n; a.k = p.k; a.f = p.f; a.logD = p.logD; a.Dk = mktfhe_ksk_rows(&p);
     a.bits64 = ctx->bits == 64; a.block = ctx->block; a.rowp = (p.n + 1 + 3) / 4 * 4;
-    if (ctx->mode == MKTFHE_MODE_STRICT || p.f * p.logD != 16 || p.logD != 2 || p.n + 1 > 32 * KS_COLS) {
+    if (ctx->mode == MKTFHE_MODE_STRICT || p.f * p.logD != 16 || p.logD != 2 || p.n + 1 > 128 * KS_J) {
         // reference loop order: one gate per CTA, parties in sequence
         const size_t smem = keyswitch_smem_bytes(ctx->N, p.f, p.n);
         k_keyswitch<<<(unsigned)gates, MK_THREADS, smem, ctx->stream>>>(a);
     } else {
         CK(cudaMemsetAsync(out, 0, gates * mktfhe_lwe_words(&p) * 4, ctx->stream));
-        const size_t smem = keyswitch_tiled_smem(ctx->N, a.rowp);
-        const dim3 grid((unsigned)((gates + KS_G - 1) / KS_G), (unsigned)p.k, KS_SPLIT);
-        if (ctx->block) {
-            CK(cudaFuncSetAttribute(k_keyswitch_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_keyswitch_tiled<true><<<grid, MK_THREADS, smem, ctx->stream>>>(a, (int)gates);
-        } else {
-            CK(cudaFuncSetAttribute(k_keyswitch_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_keyswitch_tiled<false><<<grid, MK_THREADS, smem, ctx->stream>>>(a, (int)gates);
+        auto kern = ctx->block ? k_keyswitch_tiled<true> : k_keyswitch_tiled<false>;
+        // Split the coefficient range over blockIdx.z so that the grid fills whole waves: cost of a split = rounds x
+        // co-resident CTAs x coefficients per CTA (an SM's row throughput is shared by its resident CTAs).
+        const int c_total = ctx->N - (ctx->block ? p.n : 0);
+        const size_t tiles = (gates + KS_G - 1) / KS_G;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)keyswitch_tiled_smem(c_total, a.rowp)));
+        int best_split = 1;
+        double best_cost = 1e300;
+        for (int split = 1; split <= 8; split++) {
+            const int c_per = (c_total + split - 1) / split;
+            int resident = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, MK_THREADS, keyswitch_tiled_smem(c_per, a.rowp)));
+            if (resident < 1) continue;
+            const double ctas = (double)tiles * p.k * split, slots = (double)resident * ctx->sms;
+            const double rounds = std::ceil(ctas / slots);
+            const double cost = rounds * std::min((double)resident, std::ceil(ctas / ctx->sms)) * c_per;
+            if (cost < best_cost * 0.999) { best_cost = cost; best_split = split; }
         }
+        const int c_per = (c_total + best_split - 1) / best_split;
+        const dim3 grid((unsigned)tiles, (unsigned)p.k, (unsigned)best_split);
+        kern<<<grid, MK_THREADS, keyswitch_tiled_smem(c_per, a.rowp), ctx->stream>>>(a, (int)gates, best_split);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -396,6 +410,7 @@ int mktfhe_ctx_create(const mktfhe_params *params, int device, mktfhe_ctx **out)
     ctx->pubb.assign(ctx->nparties, nullptr); ctx->ksk.assign(ctx->nparties, nullptr);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, MKTFHE_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
     *out = ctx;
     return 0;
 }

@@ -134,7 +134,7 @@ static inline size_t keyswitch_smem_bytes(int N, int f, int n) { return (size_t)
 // shared-memory reads -- a warp-uniform choice, so there is no predicated-off work.  Digits of the tile are staged as
 // 2-bit fields (f*logD = 16 bits per coefficient).  Integer adds commute: per-party partial sums of b are combined
 // with atomicAdd into a zeroed output.
-constexpr int KS_G = 16, KS_GW = 2, KS_COLS = 22, KS_STAGES = 6, KS_SPLIT = 2;     // 22 * 32 = 704 >= n + 1 for every set in params.jl
+constexpr int KS_G = 32, KS_GW = 4, KS_J = 6, KS_STAGES = 6;     // lane owns words 4*lane + 128*j: 6 * 128 = 768 >= n + 1 for every set in params.jl
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
@@ -153,19 +153,18 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 
 template <bool BLOCK>
-__global__ void __launch_bounds__(MK_THREADS) k_keyswitch_tiled(const KsArgs a, int batch) {
+__global__ void __launch_bounds__(MK_THREADS) k_keyswitch_tiled(const KsArgs a, int batch, int split) {
     constexpr int G = KS_G, DK = BLOCK ? 2 : 3, S = KS_STAGES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // the coefficient range [c_begin, N) is split over blockIdx.z; each CTA stages only its own coefficients' digits
-    const int c_all = BLOCK ? a.n : 0, c_per = (a.N - c_all + KS_SPLIT - 1) / KS_SPLIT;
+    // the coefficient range [c_all, N) is split over blockIdx.z; each CTA stages only its own coefficients' digits
+    const int c_all = BLOCK ? a.n : 0, c_per = (a.N - c_all + split - 1) / split;
     const int c_begin = c_all + (int)blockIdx.z * c_per, c_end = min(a.N, c_begin + c_per);
     uint16_t *dig = reinterpret_cast<uint16_t *>(smem_raw);                                  // [c_per][G]
-    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw + (size_t)((a.N + KS_SPLIT - 1) / KS_SPLIT) * G * sizeof(uint16_t));   // [S][DK][rowp]
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw + ((size_t)c_per * G * sizeof(uint16_t) + 15) / 16 * 16);   // [S][DK][rowp]
     __shared__ __align__(8) uint64_t full[S];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, p = blockIdx.y, g0 = blockIdx.x * G;
     const int N = a.N, n = a.n, f = a.f, row = n + 1, rowp = a.rowp;
     const int ng = min(G, batch - g0);
-    const int ncol = (row + 31) / 32;
     auto A = [&](int g, int comp, int c) -> uint32_t {
         const size_t off = ((size_t)(g0 + g) * (a.k + 1) + comp) * N + c;
         return a.bits64 ? (uint32_t)(reinterpret_cast<const uint64_t *>(a.acc)[off] >> 32)
@@ -212,11 +211,13 @@ __global__ void __launch_bounds__(MK_THREADS) k_keyswitch_tiled(const KsArgs a, 
     };
     if (tid == 0) for (int it = 0; it < S - 1 && it < steps; it++) issue(it);
 
-    uint32_t sum[KS_GW][KS_COLS];
+    // lane owns words 4*lane + 128*j .. +3 of the LWE row (16-byte shared-memory reads); jn = live j range of this lane
+    uint4 sum[KS_GW][KS_J];
 #pragma unroll
     for (int gw = 0; gw < KS_GW; gw++)
 #pragma unroll
-        for (int j = 0; j < KS_COLS; j++) sum[gw][j] = 0u;
+        for (int j = 0; j < KS_J; j++) sum[gw][j] = make_uint4(0u, 0u, 0u, 0u);
+    const int jn = 4 * lane < rowp ? (rowp - 4 * lane + 127) / 128 : 0;
 
     if (tid == 0 && S - 1 < steps) issue(S - 1);       // (the loop below refills two stages per barrier)
     for (int it = 0; it < steps; it++) {
@@ -230,22 +231,25 @@ __global__ void __launch_bounds__(MK_THREADS) k_keyswitch_tiled(const KsArgs a, 
         mbar_wait(&full[it % S], (uint32_t)((it / S) & 1));
         const uint32_t *cur = stage + (size_t)(it % S) * DK * rowp;
         const int ci = it / f, sh = 2 * (f - 1 - it % f);
+        const uint2 dpack = *reinterpret_cast<const uint2 *>(&dig[ci * G + warp * KS_GW]);      // the warp's four gates
 #pragma unroll
         for (int gw = 0; gw < KS_GW; gw++) {
-            const uint32_t d = ((uint32_t)dig[ci * G + warp * KS_GW + gw] >> sh) & 3u;       // uniform over the warp
+            const uint32_t dw = gw < 2 ? dpack.x : dpack.y;
+            const uint32_t d = (((gw & 1) ? dw >> 16 : dw & 0xFFFFu) >> sh) & 3u;              // uniform over the warp
             if (d == 0) continue;
-            if (!BLOCK) {
-                const uint32_t *r = cur + (d - 1) * rowp + lane;
+            // unbalanced: +row d-1.  balanced: d = 1: +row 0; d = 3 (-1): -row 0; d = 2 (-2): -row 1
+            const uint4 *r = reinterpret_cast<const uint4 *>(cur + (BLOCK ? (d == 2 ? 1 : 0) : (int)d - 1) * rowp) + lane;
+            if (!BLOCK || d == 1) {
 #pragma unroll
-                for (int j = 0; j < KS_COLS; j++) if (j < ncol) sum[gw][j] += r[32 * j];
-            } else {                                                    // d = 1: +row 1; d = 3 (-1): -row 1; d = 2 (-2): -row 2
-                const uint32_t *r = cur + (d == 2 ? 1 : 0) * rowp + lane;
-                if (d == 1) {
+                for (int j = 0; j < KS_J; j++) if (j < jn) {
+                    const uint4 v = r[32 * j];
+                    sum[gw][j].x += v.x; sum[gw][j].y += v.y; sum[gw][j].z += v.z; sum[gw][j].w += v.w;
+                }
+            } else {
 #pragma unroll
-                    for (int j = 0; j < KS_COLS; j++) if (j < ncol) sum[gw][j] += r[32 * j];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < KS_COLS; j++) if (j < ncol) sum[gw][j] -= r[32 * j];
+                for (int j = 0; j < KS_J; j++) if (j < jn) {
+                    const uint4 v = r[32 * j];
+                    sum[gw][j].x -= v.x; sum[gw][j].y -= v.y; sum[gw][j].z -= v.z; sum[gw][j].w -= v.w;
                 }
             }
         }
@@ -255,16 +259,20 @@ __global__ void __launch_bounds__(MK_THREADS) k_keyswitch_tiled(const KsArgs a, 
         const int g = warp * KS_GW + gw;
         if (g >= ng) continue;
         uint32_t *out = a.out + (size_t)(g0 + g) * (1 + (size_t)n * a.k);
+        const bool first = blockIdx.z == 0;
 #pragma unroll
-        for (int j = 0; j < KS_COLS; j++) {
-            const int col = lane + 32 * j;
-            const bool first = blockIdx.z == 0;
-            if (col == 0) atomicAdd(out, sum[gw][j] + (p == 0 && first ? A(g, 0, 0) : 0u));  // res.b = acc.b[0] + sum of parts
-            else if (col < row) atomicAdd(out + 1 + (size_t)p * n + (col - 1), sum[gw][j] + ((BLOCK && first && col - 1 < n) ? extract(g, col - 1) : 0u));
+        for (int j = 0; j < KS_J; j++) {
+            const uint32_t w4[4] = {sum[gw][j].x, sum[gw][j].y, sum[gw][j].z, sum[gw][j].w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int col = 4 * lane + 128 * j + q;
+                if (col == 0) atomicAdd(out, w4[q] + (p == 0 && first ? A(g, 0, 0) : 0u));  // res.b = acc.b[0] + sum of parts
+                else if (col < row) atomicAdd(out + 1 + (size_t)p * n + (col - 1), w4[q] + ((BLOCK && first && col - 1 < n) ? extract(g, col - 1) : 0u));
+            }
         }
     }
 }
-// digits + S stages of DK rows + slack so that the 32-wide column reads of the last row stay inside the allocation
-static inline size_t keyswitch_tiled_smem(int N, int rowp) {
-    return (size_t)((N + KS_SPLIT - 1) / KS_SPLIT) * KS_G * sizeof(uint16_t) + (size_t)KS_STAGES * 3 * rowp * 4 + 32 * KS_COLS * 4;
+// digits of one coefficient slice + S stages of DK rows
+static inline size_t keyswitch_tiled_smem(int c_per, int rowp) {
+    return ((size_t)c_per * KS_G * sizeof(uint16_t) + 15) / 16 * 16 + (size_t)KS_STAGES * 3 * rowp * 4;
 }
