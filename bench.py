@@ -33,7 +33,7 @@ GATE_SEED = 0x47415445
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default batch, from `ncu` captures committed under
 # profiles/ (r1_traffic_kms2.csv); null for workloads not captured.
-TRAFFIC = {"kms2": {"phase1": 5345095424 + 415138048, "keyswitch": 505005056 + 26237440, "phase2": 405425152 + 423150080}}
+TRAFFIC = {"kms2": {"phase1": 5345095424 + 415138048, "keyswitch": 441685504 + 64543488, "phase2": 405425152 + 423150080}}
 
 WORKLOADS = {  # name -> (parameter set, default per-GPU batch)
     "kms2": ("KMS2party", 4096),
@@ -362,7 +362,7 @@ def main():
                                       "peak_source": src, "traffic": TRAFFIC.get(args.workload, {}).get("keyswitch"),
                                       "kernel_ms_per_launch": ks_ms,
                                       "note": "algorithmic bytes = ksk rows gathered per gate (SURVEY 8(d)); the tiled kernel fetches each row once "
-                                              "per 16 gates, so achieved exceeds the DRAM peak and traffic is far below the algorithmic bytes"}
+                                              "per 32 gates, so achieved exceeds the DRAM peak and traffic is far below the algorithmic bytes"}
         if world == 1 and not args.no_cpu_baseline:
             info, _, _ = cpu_baseline(ks, c1, c2)
             line["cpu_baseline"] = info
