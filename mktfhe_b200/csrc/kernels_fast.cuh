@@ -728,6 +728,37 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tm_base_s));
 }
 
+// (X^a - 1)/H at the 16 slots of a thread without 16 complex multiplications.  Slot 16t + e sits at the evaluation point
+// zeta_e with zeta_e^a = m1 * eps16^(a * brv4(e)), m1 = exp(-i*pi*(4*brv6(t)+1)*a/N)/H, eps16 = exp(-i*pi/8), and
+//   eps16^(a*brv4(e)) = (-i)^(a*(2*e0 + e1)) * eps16^(2a*e2) * eps16^(a*e3)            (e = e0 + 2*e1 + 4*e2 + 8*e3):
+// four base values (three multiplications) and, per slot, a quarter-turn rotation = swap + sign flips in the integer pipe.
+// The swap happens only for odd a (and e1 = 1), which is uniform over the unit: SW selects the code version.
+// Used by the non-block kernel; in the block kernel the extra live values cost more in spills than they save (measured).
+struct Mono16 {
+    cplx v[4];            // index e3 + 2*e2
+    uint32_t sx[4], sy[4];  // sign masks per class c = 2*e0 + e1
+    __device__ __forceinline__ void init(cplx m1, uint32_t a) {
+        const cplx E1 = c_e16[a & 15], E2 = c_e16[(2 * a) & 15];
+        v[0] = m1; v[1] = cmul_f(m1, E1); v[2] = cmul_f(m1, E2); v[3] = cmul_f(v[2], E1);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint32_t q = (a * c) & 3;                 // multiply by (-i)^q
+            sx[c] = (q >> 1) << 31;
+            sy[c] = (((q + 1) >> 1) & 1) << 31;
+        }
+    }
+    template <bool SW> __device__ __forceinline__ cplx at(int e) const {
+        const int e0 = e & 1, e1 = (e >> 1) & 1, c = 2 * e0 + e1;
+        const cplx b = v[((e >> 3) & 1) + 2 * ((e >> 2) & 1)];
+        double x = (SW && e1) ? b.y : b.x, y = (SW && e1) ? b.x : b.y;
+        if (c) {
+            x = __hiloint2double(__double2hiint(x) ^ (int)sx[c], __double2loint(x));
+            y = __hiloint2double(__double2hiint(y) ^ (int)sy[c], __double2loint(y));
+        }
+        return make_double2(x - 1.0 / H, y);
+    }
+};
+
 // ======================================================================================================
 // TMA variant (default): the TMEM kernel above with the bootstrapping key streamed ONCE PER CTA.
 // The four units of a CTA are chosen from the same party, so they consume the same key polynomials in the same order
@@ -737,9 +768,12 @@ __global__ void __launch_bounds__(CTA, 1) k_phase1_tm(const Args a) {
 // consumer threads read their 16 values of a tile with conflict-free 16-byte loads and release the slot.
 // Effect: L2 -> SM key traffic drops 4x (it was 1.3 TB per 4096-gate launch, 5.4 TB/s), key values no longer occupy
 // 128 registers per thread, and their latency is hidden by the ring instead of by the scheduler.
-constexpr int RING = 5, TILE = H;                                        // tile = one polynomial, 16 KiB
+constexpr int RING_BYTES = 5 * H * 16;                                     // 80 KiB of key tiles in flight
+// tile = one polynomial (16 KiB, 5 slots) for the plain kernel, half a polynomial (slots e < 8 / e >= 8 of every thread,
+// 8 KiB, 10 slots) for the block kernel, whose fold then needs 8 + 8 instead of 16 + 16 complex accumulators
+template <int ELL> struct TileCfg { static constexpr int TILE = ELL == 1 ? H : H / 2, RING = RING_BYTES / (TILE * 16); };
 constexpr int CTA_TMA = CTA + 128;                                   // 2 consumer warpgroups + 1 producer warpgroup
-constexpr size_t SMEM_BYTES_TMA = U * SMEM_UNIT_TM + (size_t)(128 + 128 + 256) * 16 + (size_t)RING * TILE * 16 + 128;
+constexpr size_t SMEM_BYTES_TMA = U * SMEM_UNIT_TM + (size_t)(128 + 128 + 256) * 16 + (size_t)RING_BYTES + 256;
 
 __device__ __forceinline__ void mb_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
@@ -763,6 +797,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 template <int ELL>
 __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TILE = TileCfg<ELL>::TILE, RING = TileCfg<ELL>::RING, HALVES = H / TILE;
     const int tid = threadIdx.x, warp = tid >> 5, unit_l = tid / UT, t = tid % UT;
     cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + U * SMEM_UNIT_TM), *tw8 = tw2 + 128, *tw9e = tw8 + 128;
     cplx *ring = tw9e + 256;
@@ -795,7 +830,7 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
     const size_t per_idx = (size_t)4 * l * H;
     const int nsteps = a.step_mode ? 1 : (ELL == 1 ? a.n : a.d);
     const cplx *brk = a.brk[party];
-    const uint32_t ntiles = (uint32_t)nsteps * 2 * l * ELL * 2;
+    const uint32_t ntiles = (uint32_t)nsteps * 2 * l * HALVES * ELL * 2;
 
     // The register file is partitioned per scheduler (16K registers each), so a ninth warp at 200+ registers does not
     // fit: the CTA is launched with 12 warps at <= 168 registers and the warpgroups re-split the pool (setmaxnreg):
@@ -807,10 +842,12 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
             for (uint32_t n = 0; n < ntiles; n++) {
                 const int slot = n % RING;
                 if (n >= RING) mb_wait(&empty[slot], ((n / RING) - 1) & 1);
-                const uint32_t comp = n & 1, b = (n >> 1) % ELL, dg = ((n >> 1) / ELL) % (2 * l), step = (n >> 1) / ELL / (2 * l);
+                // tile n = ((((step * 2l + dg) * HALVES + half) * ELL + b) * 2 + comp)
+                const uint32_t comp = n & 1, b = (n >> 1) % ELL, hf = ((n >> 1) / ELL) % HALVES;
+                const uint32_t dg = ((n >> 1) / ELL / HALVES) % (2 * l), step = (n >> 1) / ELL / HALVES / (2 * l);
                 const int idx = (a.step_mode ? a.step_idx : (int)step) * ELL + (int)b;
                 mb_expect_tx(&full[slot], TILE * 16);
-                bulk_g2s(ring + (size_t)slot * TILE, brk + (size_t)idx * per_idx + (size_t)(dg * 2 + comp) * H, TILE * 16, &full[slot]);
+                bulk_g2s(ring + (size_t)slot * TILE, brk + (size_t)idx * per_idx + (size_t)(dg * 2 + comp) * H + (size_t)hf * TILE, TILE * 16, &full[slot]);
             }
         }
     } else {
@@ -875,7 +912,7 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
 #pragma unroll
             for (int b = 0; b < ELL; b++) { atv[b] = live ? at_src[(a.step_mode ? 0 : step * ELL) + b] : 0u; any |= atv[b] > 0; }
             if (!any) {                                        // :413 / dead unit: keep the ring moving, compute nothing
-                for (int i = 0; i < 2 * l * ELL * 2; i++) { tile_wait(); tile_done(); }
+                for (int i = 0; i < 2 * l * HALVES * ELL * 2; i++) { tile_wait(); tile_done(); }
                 continue;
             }
             cplx m1v[ELL];
@@ -905,54 +942,77 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                     }
                 }
                 fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
-                cplx kcb[16], kca[16];
                 if (ELL == 1) {
+                    // both key tiles stay in the ring while the four chunks are processed: key values are read four at a
+                    // time right before use instead of occupying 128 registers
                     const cplx *kb = tile_wait();
-#pragma unroll
-                    for (int e = 0; e < 16; e++) kcb[e] = kb[e * UT];
-                    tile_done();
+                    const int slot_b = tile_n % RING;
+                    tile_n++;
                     const cplx *ka = tile_wait();
 #pragma unroll
-                    for (int e = 0; e < 16; e++) kca[e] = ka[e * UT];
+                    for (int c = 0; c < 4; c++) {
+                        cplx zb[4], za[4], kcb[4], kca[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { kcb[i] = kb[(4 * c + i) * UT]; kca[i] = ka[(4 * c + i) * UT]; }
+                        if (dg == 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) { zb[i] = cmul_f(x[4 * c + i], kcb[i]); za[i] = cmul_f(x[4 * c + i], kca[i]); }
+                        } else {
+                            tm_ld_c4(tm + TM_TACC_B + 16 * c, zb);
+                            tm_ld_c4(tm + TM_TACC_A + 16 * c, za);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) { zb[i] = cmac_f(zb[i], x[4 * c + i], kcb[i]); za[i] = cmac_f(za[i], x[4 * c + i], kca[i]); }
+                        }
+                        tm_st_c4(tm + TM_TACC_B + 16 * c, zb);
+                        tm_st_c4(tm + TM_TACC_A + 16 * c, za);
+                    }
+                    mb_arrive(&empty[slot_b]);
                     tile_done();
                 } else {
-                    // block: fold the monomials of the block's key bits into the keys (see k_phase1)
+                    // block: fold the monomials of the block's key bits into the keys (see k_phase1), half of the thread's
+                    // slots at a time: Sum_bit mono_bit * K_bit for e in [8*hf, 8*hf + 8), then the multiply-accumulate
 #pragma unroll
-                    for (int e = 0; e < 16; e++) kcb[e] = kca[e] = make_double2(0.0, 0.0);
+                    for (int hf = 0; hf < 2; hf++) {
+                        cplx kcb[8], kca[8];
 #pragma unroll
-                    for (int b = 0; b < ELL; b++) {
-                        const cplx *kb = tile_wait();
-                        const int slot_b = tile_n % RING;
-                        tile_n++;                                   // hold the .b tile while the .a tile is awaited
-                        const cplx *ka = tile_wait();
-                        if (atv[b] != 0) {
+                        for (int e = 0; e < 8; e++) kcb[e] = kca[e] = make_double2(0.0, 0.0);
 #pragma unroll
-                            for (int e = 0; e < 16; e++) {
-                                const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
-                                cplx mo = cmul_f(m1v[b], c_e16[(atv[b] * b4) & 15]);
-                                mo.x -= 1.0 / H;
-                                kcb[e] = cmac_f(kcb[e], mo, kb[e * UT]);
-                                kca[e] = cmac_f(kca[e], mo, ka[e * UT]);
+                        for (int b = 0; b < ELL; b++) {
+                            const cplx *kb = tile_wait();
+                            const int slot_b = tile_n % RING;
+                            tile_n++;                               // hold the .b tile while the .a tile is awaited
+                            const cplx *ka = tile_wait();
+                            if (atv[b] != 0) {
+#pragma unroll
+                                for (int eh = 0; eh < 8; eh++) {
+                                    const int e = 8 * hf + eh;
+                                    const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
+                                    cplx mo = cmul_f(m1v[b], c_e16[(atv[b] * b4) & 15]);
+                                    mo.x -= 1.0 / H;
+                                    kcb[eh] = cmac_f(kcb[eh], mo, kb[eh * UT]);
+                                    kca[eh] = cmac_f(kca[eh], mo, ka[eh * UT]);
+                                }
                             }
+                            mb_arrive(&empty[slot_b]);
+                            tile_done();
                         }
-                        mb_arrive(&empty[slot_b]);
-                        tile_done();
+#pragma unroll
+                        for (int c2 = 0; c2 < 2; c2++) {
+                            const int c = 2 * hf + c2;
+                            cplx zb[4], za[4];
+                            if (dg == 0) {
+#pragma unroll
+                                for (int i = 0; i < 4; i++) { zb[i] = cmul_f(x[4 * c + i], kcb[4 * c2 + i]); za[i] = cmul_f(x[4 * c + i], kca[4 * c2 + i]); }
+                            } else {
+                                tm_ld_c4(tm + TM_TACC_B + 16 * c, zb);
+                                tm_ld_c4(tm + TM_TACC_A + 16 * c, za);
+#pragma unroll
+                                for (int i = 0; i < 4; i++) { zb[i] = cmac_f(zb[i], x[4 * c + i], kcb[4 * c2 + i]); za[i] = cmac_f(za[i], x[4 * c + i], kca[4 * c2 + i]); }
+                            }
+                            tm_st_c4(tm + TM_TACC_B + 16 * c, zb);
+                            tm_st_c4(tm + TM_TACC_A + 16 * c, za);
+                        }
                     }
-                }
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    cplx zb[4], za[4];
-                    if (dg == 0) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) { zb[i] = cmul_f(x[4 * c + i], kcb[4 * c + i]); za[i] = cmul_f(x[4 * c + i], kca[4 * c + i]); }
-                    } else {
-                        tm_ld_c4(tm + TM_TACC_B + 16 * c, zb);
-                        tm_ld_c4(tm + TM_TACC_A + 16 * c, za);
-#pragma unroll
-                        for (int i = 0; i < 4; i++) { zb[i] = cmac_f(zb[i], x[4 * c + i], kcb[4 * c + i]); za[i] = cmac_f(za[i], x[4 * c + i], kca[4 * c + i]); }
-                    }
-                    tm_st_c4(tm + TM_TACC_B + 16 * c, zb);
-                    tm_st_c4(tm + TM_TACC_A + 16 * c, za);
                 }
                 tm_wait_st();
             }
@@ -968,12 +1028,14 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                     for (int i = 0; i < 4; i++) y[4 * c + i] = z[i];
                 }
                 if (ELL == 1) {
+                    Mono16 mg;
+                    mg.init(m1v[0], atv[0]);
+                    if (atv[0] & 1) {
 #pragma unroll
-                    for (int e = 0; e < 16; e++) {
-                        const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
-                        cplx mo = cmul_f(m1v[0], c_e16[(atv[0] * b4) & 15]);
-                        mo.x -= 1.0 / H;
-                        y[e] = cmul_f(mo, y[e]);
+                        for (int e = 0; e < 16; e++) y[e] = cmul_f(mg.at<true>(e), y[e]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) y[e] = cmul_f(mg.at<false>(e), y[e]);
                     }
                 }
                 fft_inv2(y, xa, xc, tw2, tw8, tw9e, t, unit_l);
