@@ -925,14 +925,17 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                 cplx x[16];
                 {
                     uint32_t lo[32], hi[32];
+                    {
+                        uint32_t v[4][16];
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        uint32_t v[16];
-                        tm_ld16(src + 16 * c, v);
+                        for (int c = 0; c < 4; c++) tm_ld16(src + 16 * c, v[c]);       // four loads in flight, one wait
                         tm_wait_ld();
-                        tm_pin16(v);
 #pragma unroll
-                        for (int i = 0; i < 8; i++) { lo[8 * c + i] = v[2 * i]; hi[8 * c + i] = v[2 * i + 1]; }
+                        for (int c = 0; c < 4; c++) {
+                            tm_pin16(v[c]);
+#pragma unroll
+                            for (int i = 0; i < 8; i++) { lo[8 * c + i] = v[c][2 * i]; hi[8 * c + i] = v[c][2 * i + 1]; }
+                        }
                     }
 #pragma unroll
                     for (int m = 0; m < 16; m++) {
@@ -958,10 +961,17 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
 #pragma unroll
                             for (int i = 0; i < 4; i++) { zb[i] = cmul_f(x[4 * c + i], kcb[i]); za[i] = cmul_f(x[4 * c + i], kca[i]); }
                         } else {
-                            tm_ld_c4(tm + TM_TACC_B + 16 * c, zb);
-                            tm_ld_c4(tm + TM_TACC_A + 16 * c, za);
+                            uint32_t vb[16], va[16];                    // both accumulator chunks behind one wait
+                            tm_ld16(tm + TM_TACC_B + 16 * c, vb);
+                            tm_ld16(tm + TM_TACC_A + 16 * c, va);
+                            tm_wait_ld();
+                            tm_pin16(vb); tm_pin16(va);
 #pragma unroll
-                            for (int i = 0; i < 4; i++) { zb[i] = cmac_f(zb[i], x[4 * c + i], kcb[i]); za[i] = cmac_f(za[i], x[4 * c + i], kca[i]); }
+                            for (int i = 0; i < 4; i++) {
+                                zb[i] = make_double2(__hiloint2double((int)vb[4 * i + 1], (int)vb[4 * i]), __hiloint2double((int)vb[4 * i + 3], (int)vb[4 * i + 2]));
+                                za[i] = make_double2(__hiloint2double((int)va[4 * i + 1], (int)va[4 * i]), __hiloint2double((int)va[4 * i + 3], (int)va[4 * i + 2]));
+                                zb[i] = cmac_f(zb[i], x[4 * c + i], kcb[i]); za[i] = cmac_f(za[i], x[4 * c + i], kca[i]);
+                            }
                         }
                         tm_st_c4(tm + TM_TACC_B + 16 * c, zb);
                         tm_st_c4(tm + TM_TACC_A + 16 * c, za);
@@ -1004,10 +1014,17 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
 #pragma unroll
                                 for (int i = 0; i < 4; i++) { zb[i] = cmul_f(x[4 * c + i], kcb[4 * c2 + i]); za[i] = cmul_f(x[4 * c + i], kca[4 * c2 + i]); }
                             } else {
-                                tm_ld_c4(tm + TM_TACC_B + 16 * c, zb);
-                                tm_ld_c4(tm + TM_TACC_A + 16 * c, za);
+                                uint32_t vb[16], va[16];                // both accumulator chunks behind one wait
+                                tm_ld16(tm + TM_TACC_B + 16 * c, vb);
+                                tm_ld16(tm + TM_TACC_A + 16 * c, va);
+                                tm_wait_ld();
+                                tm_pin16(vb); tm_pin16(va);
 #pragma unroll
-                                for (int i = 0; i < 4; i++) { zb[i] = cmac_f(zb[i], x[4 * c + i], kcb[4 * c2 + i]); za[i] = cmac_f(za[i], x[4 * c + i], kca[4 * c2 + i]); }
+                                for (int i = 0; i < 4; i++) {
+                                    zb[i] = make_double2(__hiloint2double((int)vb[4 * i + 1], (int)vb[4 * i]), __hiloint2double((int)vb[4 * i + 3], (int)vb[4 * i + 2]));
+                                    za[i] = make_double2(__hiloint2double((int)va[4 * i + 1], (int)va[4 * i]), __hiloint2double((int)va[4 * i + 3], (int)va[4 * i + 2]));
+                                    zb[i] = cmac_f(zb[i], x[4 * c + i], kcb[4 * c2 + i]); za[i] = cmac_f(za[i], x[4 * c + i], kca[4 * c2 + i]);
+                                }
                             }
                             tm_st_c4(tm + TM_TACC_B + 16 * c, zb);
                             tm_st_c4(tm + TM_TACC_A + 16 * c, za);
@@ -1020,12 +1037,18 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
 #pragma unroll 1
             for (int pz = 0; pz < 2; pz++) {
                 cplx y[16];
+                {
+                    uint32_t v[4][16];
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    cplx z[4];
-                    tm_ld_c4(tm + (pz == 0 ? TM_TACC_B : TM_TACC_A) + 16 * c, z);
+                    for (int c = 0; c < 4; c++) tm_ld16(tm + (pz == 0 ? TM_TACC_B : TM_TACC_A) + 16 * c, v[c]);
+                    tm_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 4; i++) y[4 * c + i] = z[i];
+                    for (int c = 0; c < 4; c++) {
+                        tm_pin16(v[c]);
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            y[4 * c + i] = make_double2(__hiloint2double((int)v[c][4 * i + 1], (int)v[c][4 * i]), __hiloint2double((int)v[c][4 * i + 3], (int)v[c][4 * i + 2]));
+                    }
                 }
                 if (ELL == 1) {
                     Mono16 mg;
@@ -1040,20 +1063,21 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                 }
                 fft_inv2(y, xa, xc, tw2, tw8, tw9e, t, unit_l);
                 const uint32_t dst = tm + (pz == 0 ? TM_ACC_B : TM_ACC_A);
+                uint32_t v[4][16];
+                tm_ld16(dst, v[0]);
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    uint32_t v[16];
-                    tm_ld16(dst + 16 * c, v);
                     tm_wait_ld();
-                    tm_pin16(v);
+                    tm_pin16(v[c]);
+                    if (c < 3) tm_ld16(dst + 16 * (c + 1), v[c + 1]);           // next chunk in flight during the rounding
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int ci = 8 * c + i, m = ci & 15;
                         const uint64_t add = d2torus(ci < 16 ? y[m].x : -y[m].y);
-                        const uint64_t w = (((uint64_t)v[2 * i + 1] << 32) | v[2 * i]) + add;
-                        v[2 * i] = (uint32_t)w; v[2 * i + 1] = (uint32_t)(w >> 32);
+                        const uint64_t w = (((uint64_t)v[c][2 * i + 1] << 32) | v[c][2 * i]) + add;
+                        v[c][2 * i] = (uint32_t)w; v[c][2 * i + 1] = (uint32_t)(w >> 32);
                     }
-                    tm_st16(dst + 16 * c, v);
+                    tm_st16(dst + 16 * c, v[c]);
                 }
                 tm_wait_st();
             }
