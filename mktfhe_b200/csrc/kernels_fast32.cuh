@@ -137,7 +137,7 @@ struct Args {
     size_t units;
 };
 
-constexpr size_t SMEM_UNIT = (size_t)2 * N * 4 + (size_t)2 * XB_LEN * 16;       // acc (b, a) + two exchange buffers
+constexpr size_t SMEM_UNIT = (size_t)2 * XB_LEN * 16;                           // two exchange buffers (accumulators live in TMEM)
 constexpr size_t SMEM_BYTES = U * SMEM_UNIT + (size_t)(32 + 256) * 16 + 16;
 
 template <int ELL>
@@ -147,36 +147,42 @@ __global__ void __launch_bounds__(CTA, 1) k_rgsw_tm(const Args a) {
     cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + U * SMEM_UNIT), *tw3 = tw2 + 32;
     uint32_t *tm_base_s = reinterpret_cast<uint32_t *>(tw3 + 256);
     for (int i = tid; i < 256; i += CTA) { if (i < 32) tw2[i] = a.tb.t2[i]; tw3[i] = a.tb.t3[i]; }
-    uint32_t *accb = reinterpret_cast<uint32_t *>(smem_raw + unit_l * SMEM_UNIT), *acca = accb + N;
-    cplx *xa = reinterpret_cast<cplx *>(acca + N), *xc = xa + XB_LEN;
+    cplx *xa = reinterpret_cast<cplx *>(smem_raw + unit_l * SMEM_UNIT), *xc = xa + XB_LEN;
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"((uint32_t)__cvta_generic_to_shared(tm_base_s)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"((uint32_t)__cvta_generic_to_shared(tm_base_s)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
-    // warp w -> lanes 32*(w%4).., columns 64*(w/4)..; per thread: tacc.b = columns [0,32), tacc.a = [32,64)
-    const uint32_t tm = *tm_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + 64u * (uint32_t)(warp >> 2);
+    // warp w -> lanes 32*(w%4).., columns 96*(w/4)..; per thread: tacc.b = columns [0,32), tacc.a = [32,64),
+    // acc.b = [64,80), acc.a = [80,96): word m of a row is coefficient t + 64m (only this thread ever touches it)
+    const uint32_t tm = *tm_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + 96u * (uint32_t)(warp >> 2);
+    constexpr uint32_t TM_ACCB = 64, TM_ACCA = 80;
 
     const size_t unit = (size_t)blockIdx.x * U + unit_l;
     if (unit < a.units) {
         const int gate = (int)unit;
-        if (!a.step_mode) {                    // test vector: bootstrapping.jl:11-23
-            const uint32_t tb = a.tilde[(size_t)gate * a.lwe_words];
-            const uint32_t e8 = 1u << 29;
+        {
+            uint32_t vb[16], va[16];
+            if (!a.step_mode) {                    // test vector: bootstrapping.jl:11-23
+                const uint32_t tb = a.tilde[(size_t)gate * a.lwe_words];
+                const uint32_t e8 = 1u << 29;
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const uint32_t i1 = (uint32_t)(t + 64 * m) + 1;      // 1-based coefficient index
-                accb[t + 64 * m] = tb <= (uint32_t)N ? (i1 <= tb ? e8 : 0u - e8) : (i1 <= tb - (uint32_t)N ? 0u - e8 : e8);
-                acca[t + 64 * m] = 0u;
+                for (int m = 0; m < 16; m++) {
+                    const uint32_t i1 = (uint32_t)(t + 64 * m) + 1;      // 1-based coefficient index
+                    vb[m] = tb <= (uint32_t)N ? (i1 <= tb ? e8 : 0u - e8) : (i1 <= tb - (uint32_t)N ? 0u - e8 : e8);
+                    va[m] = 0u;
+                }
+            } else {
+                const uint32_t *src = a.acc_io + unit * 2 * N;
+#pragma unroll
+                for (int m = 0; m < 16; m++) { vb[m] = src[t + 64 * m]; va[m] = src[N + t + 64 * m]; }
             }
-        } else {
-            const uint32_t *src = a.acc_io + unit * 2 * N;
-#pragma unroll
-            for (int m = 0; m < 16; m++) { accb[t + 64 * m] = src[t + 64 * m]; acca[t + 64 * m] = src[N + t + 64 * m]; }
+            fast::tm_st16(tm + TM_ACCB, vb);
+            fast::tm_st16(tm + TM_ACCA, va);
+            tm_wait_st();
         }
-        // thread t only touches coefficients t + 64m of its unit: no barrier needed around the accumulator
 
         const int l = a.l, logB = a.logB;
         const int bit = 32 - l * logB;
@@ -203,13 +209,18 @@ __global__ void __launch_bounds__(CTA, 1) k_rgsw_tm(const Args a) {
             for (int b = 0; b < ELL; b++) m1v[b] = __ldg(&a.tb.emono[((4 * brv6t + 1) * atv[b]) & 2047]);
 
             for (int dg = 0; dg < 2 * l; dg++) {
-                const uint32_t *src = dg < l ? accb : acca;
                 const int sh = bit + (l - 1 - (dg < l ? dg : dg - l)) * logB;
                 cplx x[8];
+                {
+                    uint32_t v[16];
+                    fast::tm_ld16(tm + (dg < l ? TM_ACCB : TM_ACCA), v);
+                    fast::tm_wait_ld();
+                    fast::tm_pin16(v);
 #pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    const uint32_t f0 = ((src[t + 64 * m] + cadd) >> sh) & mask, f1 = ((src[t + 64 * m + H] + cadd) >> sh) & mask;
-                    x[m] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
+                    for (int m = 0; m < 8; m++) {
+                        const uint32_t f0 = ((v[m] + cadd) >> sh) & mask, f1 = ((v[m + 8] + cadd) >> sh) & mask;
+                        x[m] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
+                    }
                 }
                 const cplx *kb = kidx + (size_t)(dg * 2) * H, *ka = kb + H;
                 cplx kcb[8], kca[8];
@@ -274,21 +285,32 @@ __global__ void __launch_bounds__(CTA, 1) k_rgsw_tm(const Args a) {
                     }
                 }
                 fft_inv(y, xa, xc, tw2, tw3, t, unit_l);
-                uint32_t *dst = pz == 0 ? accb : acca;
+                {
+                    uint32_t v[16];
+                    fast::tm_ld16(tm + (pz == 0 ? TM_ACCB : TM_ACCA), v);
+                    fast::tm_wait_ld();
+                    fast::tm_pin16(v);
 #pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    dst[t + 64 * m] += d2torus32(y[m].x);
-                    dst[t + 64 * m + H] += d2torus32(-y[m].y);
+                    for (int m = 0; m < 8; m++) { v[m] += d2torus32(y[m].x); v[m + 8] += d2torus32(-y[m].y); }
+                    fast::tm_st16(tm + (pz == 0 ? TM_ACCB : TM_ACCA), v);
+                    tm_wait_st();
                 }
             }
         }
         uint32_t *out = a.acc_io + unit * 2 * N;
+        {
+            uint32_t vb[16], va[16];
+            fast::tm_ld16(tm + TM_ACCB, vb);
+            fast::tm_ld16(tm + TM_ACCA, va);
+            fast::tm_wait_ld();
+            fast::tm_pin16(vb); fast::tm_pin16(va);
 #pragma unroll
-        for (int m = 0; m < 16; m++) { out[t + 64 * m] = accb[t + 64 * m]; out[N + t + 64 * m] = acca[t + 64 * m]; }
+            for (int m = 0; m < 16; m++) { out[t + 64 * m] = vb[m]; out[N + t + 64 * m] = va[m]; }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(*tm_base_s));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tm_base_s));
 }
 
 // reference slot order [poly][8t + e] -> thread order [poly][e][t]

@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(MK_THREADS) k_keyswitch_tiled(const KsArgs a, 
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw + ((size_t)c_per * G * sizeof(uint16_t) + 15) / 16 * 16);   // [S][DK][rowp]
     __shared__ __align__(8) uint64_t full[S];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, p = blockIdx.y, g0 = blockIdx.x * G;
-    const int N = a.N, n = a.n, f = a.f, row = n + 1, rowp = a.rowp;
+    constexpr int f = 8;                         // the launcher takes this kernel only for f = 8, logD = 2 (every set in params.jl)
+    const int N = a.N, n = a.n, row = n + 1, rowp = a.rowp;
     const int ng = min(G, batch - g0);
     auto A = [&](int g, int comp, int c) -> uint32_t {
         const size_t off = ((size_t)(g0 + g) * (a.k + 1) + comp) * N + c;
