@@ -39,8 +39,8 @@ WORKLOADS = {  # name -> (parameter set, default per-GPU batch)
     "kms2": ("KMS2party", 4096),
     "kms8block": ("KMS8partyblock", 2048),
     "kms8": ("KMS8party", 1024),
-    "kms32": ("KMS32party", 128),
-    "kms32block": ("KMS32partyblock", 128),
+    "kms32": ("KMS32party", 1024),
+    "kms32block": ("KMS32partyblock", 1024),
     "cggi": ("CGGIparam", 4096),
     "lmss": ("Blockparam", 4096),
     "ccs2": ("CCS2party", 1024),

@@ -239,9 +239,15 @@ int run_blindrotate(mktfhe_ctx *ctx, const uint32_t *tilde, size_t gates, StageE
     const mktfhe_params &p = ctx->p;
     int rc;
     if (ctx->kms) {
-        if ((rc = run_phase1(ctx, tilde, ctx->w_lev, gates))) return rc;
+        // FAST: both phases in the production kernels; the RLEV rows travel between them in thread order
+        const bool fast2 = ctx->mode == MKTFHE_MODE_FAST && fast_supported(p) && fast_variant_tma();
+        if (fast2) rc = fast_phase1(ctx->fast, p, tilde, ctx->w_lev, gates, ctx->stream, &ctx->launches, ctx->err, true);
+        else rc = run_phase1(ctx, tilde, ctx->w_lev, gates);
+        if (rc) return rc;
         if (ev) cudaEventRecord(ev->e[2], ctx->stream);
-        if ((rc = run_phase2(ctx, tilde, ctx->w_lev, (uint64_t *)ctx->w_acc, gates))) return rc;
+        if (fast2) rc = fast_phase2(ctx->fast, p, tilde, ctx->w_lev, (uint64_t *)ctx->w_acc, ctx->w_tx, ctx->w_ty, gates, ctx->stream, &ctx->launches, ctx->err);
+        else rc = run_phase2(ctx, tilde, ctx->w_lev, (uint64_t *)ctx->w_acc, gates);
+        if (rc) return rc;
     } else if (p.scheme == MKTFHE_CCS) {
         if (ctx->mode == MKTFHE_MODE_FAST && fastccs_supported(p))
             rc = fastccs_launch(ctx->fastccs, ctx->fast32, p, tilde, (uint32_t *)ctx->w_acc, ctx->w_tx, gates, ctx->stream, &ctx->launches, ctx->err);
@@ -504,7 +510,7 @@ int mktfhe_finalize_keys(mktfhe_ctx *ctx) {
         k_build_monomials<512><<<(2 * ctx->N + G - 1) / G, MK_THREADS, smem, ctx->stream>>>(ctx->mono, ctx->tables());
     }
     CK(cudaGetLastError());
-    if (fast_supported(ctx->p) && (rc = fast_build(ctx->fast, ctx->p, ctx->brk, ctx->stream, ctx->err))) return rc;
+    if (fast_supported(ctx->p) && (rc = fast_build(ctx->fast, ctx->p, ctx->brk, ctx->rlk, ctx->pubb, ctx->crs, ctx->stream, ctx->err))) return rc;
     if (fast32_supported(ctx->p) && (rc = fast32_build(ctx->fast32, ctx->p, ctx->brk[0], ctx->stream, ctx->err))) return rc;
     if (fastccs_supported(ctx->p)) {
         if ((rc = fast32_build(ctx->fast32, ctx->p, nullptr, ctx->stream, ctx->err))) return rc;      // transform tables only

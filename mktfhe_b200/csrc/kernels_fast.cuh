@@ -220,7 +220,8 @@ struct Args {
     const uint32_t *tilde;        // [B][lwe_words] (phase 1) / [units] rotations (step mode)
     const cplx *const *brk;       // [k] FAST-layout keys: [idx][dg][comp][e][t]
     Tables tb;
-    cplx *lev_out;                // [B][R][2][H], reference slot order
+    cplx *lev_out;                // [B][R][2][H], reference slot order (lev_fast: thread order [e][t], scaled by 1/H)
+    int lev_fast;
     uint64_t *acc_io;             // step mode: [units][2][N]
     int step_mode, step_party, step_idx;
     int n, d, k, l, logB, l_lev, logB_lev, R, lwe_words;
@@ -1105,8 +1106,13 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                         x[m] = make_double2(__ll2double_rn((long long)v0), __ll2double_rn((long long)((uint64_t)0 - v1)));
                     }
                     fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+                    if (a.lev_fast) {          // for k_phase2: thread order, and the 1/H of phase 2's inverse transforms (exact)
 #pragma unroll
-                    for (int e = 0; e < 16; e++) out[(size_t)pz * H + 16 * t + e] = x[e];
+                        for (int e = 0; e < 16; e++) out[(size_t)pz * H + e * UT + t] = make_double2(x[e].x * (1.0 / H), x[e].y * (1.0 / H));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) out[(size_t)pz * H + 16 * t + e] = x[e];
+                    }
                 }
             } else {
                 uint64_t *dst = a.acc_io + up * 2 * N;
@@ -1132,6 +1138,228 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tm_base_s));
 }
 
+
+// ---- FAST phase 2 (bootstrapping.jl:448-558) ------------------------------------------------------------------------
+// One gate per 64-thread unit, four gates per CTA, parties in sequence as in the reference.  Per party idx and
+// component c <= idx:  (tx, ty) = Sum_j D_j(acc_c) * levkey[idx][j];  y_c = ifft(ty);  u_c = Sum_j D_j(y_c) * rlk.d[j];
+// v -/+= Sum_j D_j(y_c) * (crs | pubb[c-1])[j];  then w = Sum_j D_j(ifft(v)) * rlk.f[j] and
+// acc_c = ifft(tx_c + u_c (+ w.b for c = 0)), acc_{idx+1} = ifft(w.a).
+// The four running sums (tx, ty | wb, wa, u, v) live in TMEM (64 columns each per thread), the polynomial being
+// re-decomposed stays in registers (the thread that produced coefficient t + 64m also decomposes it), tx_c and u_c wait in
+// a global scratch in thread order.  All keys are in thread order [e][t] and carry the 1/H of the inverse transform.
+struct P2Args {
+    const uint32_t *tilde;        // [B][lwe_words]; only b~ is read
+    const cplx *lev;              // [B][R][2][H] from k_phase1_tma with lev_fast
+    const cplx *const *rlk;       // [k]: [l_uni][3][H]
+    const cplx *const *pubb;      // [k]: [l_uni][H]
+    const cplx *crs;              // [l_uni][H]
+    Tables tb;
+    uint64_t *acc;                // [B][(k+1)][N] out
+    cplx *tx, *ty;                // scratch [B][(k+1)][H] each
+    int k, l_lev, logB_lev, l_uni, logB_uni, R, lwe_words;
+    size_t gates;
+};
+
+constexpr uint32_t TM2_TX = 0, TM2_TY = 64, TM2_U = 128, TM2_V = 192;
+
+// digit dg (0 = most significant) of the 32 coefficients held as (lo, hi) words: one add does the rounding and the
+// + B/2 at every digit position, then the digit is a bit field (gsw.jl:86-96)
+__device__ __forceinline__ void p2_digits(const uint32_t (&lo)[32], const uint32_t (&hi)[32], int dg, int l, int logB, cplx (&x)[16]) {
+    const int bit = 64 - l * logB;
+    uint64_t cadd = (uint64_t)1 << (bit - 1);
+    for (int j = 0; j < l; j++) cadd += (uint64_t)1 << (bit + j * logB + logB - 1);
+    const uint32_t mask = (1u << logB) - 1;
+    const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));
+    const int sh = bit + (l - 1 - dg) * logB;
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+        const uint64_t v0 = (((uint64_t)hi[m] << 32) | lo[m]) + cadd, v1 = (((uint64_t)hi[m + 16] << 32) | lo[m + 16]) + cadd;
+        const uint32_t f0 = (uint32_t)(v0 >> sh) & mask, f1 = (uint32_t)(v1 >> sh) & mask;
+        x[m] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
+    }
+}
+// two TMEM accumulators += x * (ka, kb) (thread-order keys); first_a / first_b overwrite; sb = -1 subtracts the second product
+__device__ __forceinline__ void p2_mac(uint32_t tm_a, uint32_t tm_b, const cplx (&x)[16], const cplx *ka, const cplx *kb,
+                                       bool first_a, bool first_b, double sb) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        cplx za[4], zb[4], va[4], vb[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            va[i] = __ldg(ka + (4 * c + i) * UT); vb[i] = __ldg(kb + (4 * c + i) * UT);
+            za[i] = zb[i] = make_double2(0.0, 0.0);
+        }
+        uint32_t ra[16], rb[16];
+        if (!first_a) tm_ld16(tm_a + 16 * c, ra);
+        if (!first_b) tm_ld16(tm_b + 16 * c, rb);
+        if (!first_a || !first_b) tm_wait_ld();
+        if (!first_a) {
+            tm_pin16(ra);
+#pragma unroll
+            for (int i = 0; i < 4; i++) za[i] = make_double2(__hiloint2double((int)ra[4 * i + 1], (int)ra[4 * i]), __hiloint2double((int)ra[4 * i + 3], (int)ra[4 * i + 2]));
+        }
+        if (!first_b) {
+            tm_pin16(rb);
+#pragma unroll
+            for (int i = 0; i < 4; i++) zb[i] = make_double2(__hiloint2double((int)rb[4 * i + 1], (int)rb[4 * i]), __hiloint2double((int)rb[4 * i + 3], (int)rb[4 * i + 2]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            za[i] = cmac_f(za[i], x[4 * c + i], va[i]);
+            zb[i] = cmac_f(zb[i], make_double2(sb * x[4 * c + i].x, sb * x[4 * c + i].y), vb[i]);
+        }
+        tm_st_c4(tm_a + 16 * c, za);
+        tm_st_c4(tm_b + 16 * c, zb);
+    }
+    tm_wait_st();
+}
+__device__ __forceinline__ void p2_tm_load(uint32_t tm_src, cplx (&y)[16]) {
+    uint32_t v[4][16];
+#pragma unroll
+    for (int c = 0; c < 4; c++) tm_ld16(tm_src + 16 * c, v[c]);
+    tm_wait_ld();
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        tm_pin16(v[c]);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            y[4 * c + i] = make_double2(__hiloint2double((int)v[c][4 * i + 1], (int)v[c][4 * i]), __hiloint2double((int)v[c][4 * i + 3], (int)v[c][4 * i + 2]));
+    }
+}
+__device__ __forceinline__ void p2_tm_store(uint32_t tm_dst, const cplx (&y)[16]) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        cplx z[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) z[i] = y[4 * c + i];
+        tm_st_c4(tm_dst + 16 * c, z);
+    }
+    tm_wait_st();
+}
+
+__global__ void __launch_bounds__(CTA, 1) k_phase2(const P2Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, unit_l = tid / UT, t = tid % UT;
+    cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + U * SMEM_UNIT_TM), *tw8 = tw2 + 128, *tw9e = tw8 + 128;
+    uint32_t *tm_base_s = reinterpret_cast<uint32_t *>(tw9e + 256);
+    for (int i = tid; i < 256; i += CTA) { if (i < 128) { tw2[i] = a.tb.t2[i]; tw8[i] = a.tb.t8[i]; } tw9e[i] = a.tb.t9[i]; }
+    cplx *xa = reinterpret_cast<cplx *>(smem_raw + unit_l * SMEM_UNIT_TM), *xc = xa + XB_LEN;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"((uint32_t)__cvta_generic_to_shared(tm_base_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tm = *tm_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + 256u * (uint32_t)(warp >> 2);
+
+    const size_t gate = (size_t)blockIdx.x * U + unit_l;
+    if (gate < a.gates) {
+        const int k = a.k, ll = a.l_lev, lu = a.l_uni;
+        uint64_t *ACC = a.acc + gate * (size_t)(k + 1) * N;
+        cplx *TX = a.tx + gate * (size_t)(k + 1) * H + t, *TY = a.ty + gate * (size_t)(k + 1) * H + t;
+        const cplx *LEV = a.lev + gate * (size_t)a.R * 2 * H + t;
+        uint32_t lo[32], hi[32];
+        cplx x[16];
+        // coefficient held in slot m (< 16) is t + 64m, in slot 16 + m it is t + 64m + H
+        auto load_poly = [&](const uint64_t *src) {
+#pragma unroll
+            for (int m = 0; m < 32; m++) { const uint64_t v = src[t + 64 * (m & 15) + (m >> 4) * H]; lo[m] = (uint32_t)v; hi[m] = (uint32_t)(v >> 32); }
+        };
+        auto store_poly = [&](uint64_t *dst, const cplx (&y)[16]) {
+#pragma unroll
+            for (int m = 0; m < 16; m++) { dst[t + 64 * m] = d2torus(y[m].x); dst[t + 64 * m + H] = d2torus(-y[m].y); }
+        };
+        auto to_regs = [&](const cplx (&y)[16]) {                      // native(): arithmetic.jl:6-9
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const uint64_t v0 = d2torus(y[m].x), v1 = d2torus(-y[m].y);
+                lo[m] = (uint32_t)v0; hi[m] = (uint32_t)(v0 >> 32); lo[m + 16] = (uint32_t)v1; hi[m + 16] = (uint32_t)(v1 >> 32);
+            }
+        };
+        {   // acc = (test vector, 0 ... 0): bootstrapping.jl:11-23
+            const uint32_t tb = a.tilde[gate * a.lwe_words];
+            const uint64_t e8 = (uint64_t)1 << 61;
+#pragma unroll
+            for (int m = 0; m < 32; m++) {
+                const int i0 = t + 64 * (m & 15) + (m >> 4) * H;
+                const uint32_t i1 = (uint32_t)i0 + 1;
+                ACC[i0] = tb <= (uint32_t)N ? (i1 <= tb ? e8 : (uint64_t)0 - e8) : (i1 <= tb - (uint32_t)N ? (uint64_t)0 - e8 : e8);
+            }
+            // components 1 .. k are written before they are read (component c is first read at idx = c, written at idx = c - 1)
+        }
+        for (int idx = 0; idx < k; idx++) {
+            const cplx *lk = LEV + (size_t)(idx == 0 ? 0 : 1 + (idx - 1) * ll) * 2 * H;
+            const cplx *rlk = a.rlk[idx] + t;
+            const int iter = idx == 0 ? 1 : ll;                         // :481
+            for (int c = 0; c <= idx; c++) {                            // components b, a_1 .. a_idx
+                load_poly(ACC + (size_t)c * N);
+                for (int j = 0; j < iter; j++) {                        // LEV product with levkey[idx]: :483-499
+                    p2_digits(lo, hi, j, ll, a.logB_lev, x);
+                    fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+                    p2_mac(tm + TM2_TX, tm + TM2_TY, x, lk + (size_t)(j * 2) * H, lk + (size_t)(j * 2 + 1) * H, j == 0, j == 0, 1.0);
+                }
+                p2_tm_load(tm + TM2_TX, x);
+#pragma unroll
+                for (int e = 0; e < 16; e++) TX[(size_t)c * H + e * UT] = x[e];
+                p2_tm_load(tm + TM2_TY, x);
+                fft_inv2(x, xa, xc, tw2, tw8, tw9e, t, unit_l);         // y_c: :501-504
+                to_regs(x);
+                const cplx *kv = c == 0 ? a.crs + t : a.pubb[c - 1] + t;
+                for (int j = 0; j < lu; j++) {                          // u and v: :520-535
+                    p2_digits(lo, hi, j, lu, a.logB_uni, x);
+                    fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+                    // u restarts for every component; v runs over all components of this party (first term: c = 0, j = 0)
+                    p2_mac(tm + TM2_U, tm + TM2_V, x, rlk + (size_t)(j * 3) * H, kv + (size_t)j * H, j == 0, j == 0 && c == 0, c == 0 ? -1.0 : 1.0);
+                }
+                p2_tm_load(tm + TM2_U, x);
+#pragma unroll
+                for (int e = 0; e < 16; e++) TY[(size_t)c * H + e * UT] = x[e];
+            }
+            // v -> coefficient form -> digits -> w: :538-550
+            p2_tm_load(tm + TM2_V, x);
+            fft_inv2(x, xa, xc, tw2, tw8, tw9e, t, unit_l);
+            to_regs(x);
+            for (int j = 0; j < lu; j++) {
+                p2_digits(lo, hi, j, lu, a.logB_uni, x);
+                fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+                p2_mac(tm + TM2_TX, tm + TM2_TY, x, rlk + (size_t)(j * 3 + 1) * H, rlk + (size_t)(j * 3 + 2) * H, j == 0, j == 0, 1.0);   // wb, wa
+            }
+            // acc_c = ifft(tx_c + u_c (+ wb)); acc_{idx+1} = ifft(wa): :553-556
+            for (int c = 0; c <= idx + 1; c++) {
+                if (c == idx + 1) p2_tm_load(tm + TM2_TY, x);
+                else {
+                    if (c == 0) p2_tm_load(tm + TM2_TX, x);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) x[e] = make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        const cplx p = TX[(size_t)c * H + e * UT], q = TY[(size_t)c * H + e * UT];
+                        x[e].x += p.x + q.x; x[e].y += p.y + q.y;
+                    }
+                }
+                fft_inv2(x, xa, xc, tw2, tw8, tw9e, t, unit_l);
+                store_poly(ACC + (size_t)c * N, x);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tm_base_s));
+}
+
+// reference slot order [poly][16t + e] -> thread order [poly][e][t], scaled (1/H for the phase-2 keys)
+__global__ void k_permute_scale(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys, double scale) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= polys * H) return;
+    const size_t p = i / H;
+    const int r = (int)(i % H), e = r / UT, t = r % UT;
+    const cplx v = in[p * H + 16 * t + e];
+    out[i] = make_double2(v.x * scale, v.y * scale);
+}
+
 // reference slot order [poly][16t + e] -> thread order [poly][e][t]
 __global__ void k_permute_brk(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1147,8 +1375,16 @@ struct FastKeys {
     std::vector<cplx *> brk;        // per party, FAST layout
     cplx **d_brk = nullptr;
     cplx *t2 = nullptr, *t8 = nullptr, *t9 = nullptr, *emono = nullptr;
+    // phase-2 keys in thread order, scaled by 1/H
+    std::vector<cplx *> rlk, pubb;
+    cplx **d_rlk = nullptr, **d_pubb = nullptr, *crs = nullptr;
     bool built = false;
 };
+
+static inline bool fast_variant_tma() {
+    static const bool tma = []() { const char *e = getenv("MKTFHE_FAST_KERNEL"); return !e || std::string(e) == "tma"; }();
+    return tma;
+}
 
 static inline bool fast_supported(const mktfhe_params &p) {
     return p.N == 2048 && (p.scheme == MKTFHE_KMS || (p.scheme == MKTFHE_KMS_BLOCK && p.ell == 3));
@@ -1162,7 +1398,13 @@ static inline void fast_free(FastKeys &f) {
     if (f.t8) cudaFree(f.t8);
     if (f.t9) cudaFree(f.t9);
     if (f.emono) cudaFree(f.emono);
-    f.d_brk = nullptr; f.t2 = f.t8 = f.t9 = f.emono = nullptr; f.built = false;
+    for (auto &q : f.rlk) if (q) cudaFree(q);
+    for (auto &q : f.pubb) if (q) cudaFree(q);
+    f.rlk.clear(); f.pubb.clear();
+    if (f.d_rlk) cudaFree(f.d_rlk);
+    if (f.d_pubb) cudaFree(f.d_pubb);
+    if (f.crs) cudaFree(f.crs);
+    f.d_brk = nullptr; f.t2 = f.t8 = f.t9 = f.emono = nullptr; f.d_rlk = f.d_pubb = nullptr; f.crs = nullptr; f.built = false;
 }
 
 #define FCK(call)                                                                        \
@@ -1173,7 +1415,8 @@ static inline void fast_free(FastKeys &f) {
 #define MKTFHE_ERR_CUDA_ (-2)
 
 // Twiddles sqrt(rho(s, i)) = exp(-i*pi*theta(s,i)/2): theta(0,0) = 1/2, theta(s+1, 2i+b) = theta(s,i)/2 + b.
-static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vector<cplx *> &brk_ref, cudaStream_t stream, std::string &err) {
+static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vector<cplx *> &brk_ref, const std::vector<cplx *> &rlk_ref,
+                             const std::vector<cplx *> &pubb_ref, const cplx *crs_ref, cudaStream_t stream, std::string &err) {
     using namespace fast;
     fast_free(f);
     std::vector<__float128> theta(1, (__float128)0.5);
@@ -1228,6 +1471,25 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
     FCK(cudaFuncSetAttribute(k_phase1_tm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
     FCK(cudaFuncSetAttribute(k_phase1_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TMA));
     FCK(cudaFuncSetAttribute(k_phase1_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TMA));
+    FCK(cudaFuncSetAttribute(k_phase2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
+    // phase-2 keys: thread order, 1/H folded in (a power of two: exact)
+    f.rlk.assign(rlk_ref.size(), nullptr); f.pubb.assign(pubb_ref.size(), nullptr);
+    auto permute = [&](const cplx *src, cplx *&dst, size_t npoly) -> int {
+        FCK(cudaMalloc(&dst, npoly * H * sizeof(cplx)));
+        k_permute_scale<<<(unsigned)((npoly * H + 255) / 256), 256, 0, stream>>>(src, dst, npoly, 1.0 / H);
+        FCK(cudaGetLastError());
+        return 0;
+    };
+    for (size_t i = 0; i < rlk_ref.size(); i++) {
+        int rc;
+        if ((rc = permute(rlk_ref[i], f.rlk[i], (size_t)p.l_uni * 3))) return rc;
+        if ((rc = permute(pubb_ref[i], f.pubb[i], (size_t)p.l_uni))) return rc;
+    }
+    { int rc; if ((rc = permute(crs_ref, f.crs, (size_t)p.l_uni))) return rc; }
+    FCK(cudaMalloc(&f.d_rlk, sizeof(cplx *) * f.rlk.size()));
+    FCK(cudaMalloc(&f.d_pubb, sizeof(cplx *) * f.pubb.size()));
+    FCK(cudaMemcpy(f.d_rlk, f.rlk.data(), sizeof(cplx *) * f.rlk.size(), cudaMemcpyHostToDevice));
+    FCK(cudaMemcpy(f.d_pubb, f.pubb.data(), sizeof(cplx *) * f.pubb.size(), cudaMemcpyHostToDevice));
     f.built = true;
     return 0;
 }
@@ -1240,7 +1502,7 @@ static inline int fast_launch(FastKeys &f, const mktfhe_params &p, fast::Args a,
     a.R = 1 + (p.k - 1) * p.l_lev; a.lwe_words = (int)mktfhe_lwe_words(&p);
     const unsigned grid = (unsigned)((a.units + U - 1) / U);
     a.d = p.d;
-    static const std::string variant = []() { const char *e = getenv("MKTFHE_FAST_KERNEL"); return std::string(e ? e : "tma"); }();
+    static const std::string variant = []() { const char *e = getenv("MKTFHE_FAST_KERNEL"); return std::string(e ? e : "tma"); }();      // tma | tmem | smem
     if (variant == "tma") {
         // CTAs are grouped by party (one key stream per CTA): ceil(gates/U) for party 0 plus ceil(gates*l_lev/U) per other party
         size_t ctas;
@@ -1273,12 +1535,28 @@ static inline int fast_launch(FastKeys &f, const mktfhe_params &p, fast::Args a,
     return 0;
 }
 
+// lev_fast: write the RLEV rows for k_phase2 (thread order, scaled by 1/H); only the TMA kernel implements it
 static inline int fast_phase1(FastKeys &f, const mktfhe_params &p, const uint32_t *tilde, cplx *lev, size_t gates,
-                              cudaStream_t stream, int *launches, std::string &err) {
+                              cudaStream_t stream, int *launches, std::string &err, bool lev_fast = false) {
     fast::Args a{};
-    a.tilde = tilde; a.lev_out = lev; a.step_mode = 0;
+    a.tilde = tilde; a.lev_out = lev; a.step_mode = 0; a.lev_fast = lev_fast && fast_variant_tma();
     a.units = gates * (size_t)(1 + (p.k - 1) * p.l_lev);
     return fast_launch(f, p, a, stream, launches, err);
+}
+
+static inline int fast_phase2(FastKeys &f, const mktfhe_params &p, const uint32_t *tilde, const cplx *lev, uint64_t *acc, cplx *tx, cplx *ty,
+                              size_t gates, cudaStream_t stream, int *launches, std::string &err) {
+    using namespace fast;
+    if (!f.built) { err = "FAST keys not built"; return -3; }
+    P2Args a{};
+    a.tilde = tilde; a.lev = lev; a.rlk = f.d_rlk; a.pubb = f.d_pubb; a.crs = f.crs; a.tb = Tables{f.t2, f.t8, f.t9, f.emono};
+    a.acc = acc; a.tx = tx; a.ty = ty;
+    a.k = p.k; a.l_lev = p.l_lev; a.logB_lev = p.logB_lev; a.l_uni = p.l_uni; a.logB_uni = p.logB_uni;
+    a.R = 1 + (p.k - 1) * p.l_lev; a.lwe_words = (int)mktfhe_lwe_words(&p); a.gates = gates;
+    k_phase2<<<(unsigned)((gates + U - 1) / U), CTA, SMEM_BYTES_TM, stream>>>(a);
+    if (launches) (*launches)++;
+    FCK(cudaGetLastError());
+    return 0;
 }
 
 static inline int fast_cmux_step(FastKeys &f, const mktfhe_params &p, int party, int idx, const uint32_t *atilde, void *rows,
