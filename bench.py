@@ -33,7 +33,7 @@ GATE_SEED = 0x47415445
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default batch, from `ncu` captures committed under
 # profiles/ (r1_traffic_kms2.csv); null for workloads not captured.
-TRAFFIC = {"kms2": {"phase1": 5345095424 + 415138048, "keyswitch": 441685504 + 64543488, "phase2": 405425152 + 423150080}}
+TRAFFIC = {"kms2": {"phase1": 2451908096 + 398664704, "keyswitch": 437774592 + 56238336, "phase2": 459913728 + 615687168}}
 
 WORKLOADS = {  # name -> (parameter set, default per-GPU batch)
     "kms2": ("KMS2party", 4096),
