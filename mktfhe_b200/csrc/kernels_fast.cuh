@@ -435,6 +435,105 @@ constexpr int TM_ACC_B = 0, TM_ACC_A = 64, TM_TACC_B = 128, TM_TACC_A = 192;
 constexpr size_t SMEM_UNIT_TM = (size_t)2 * XB_LEN * 16;                                   // two exchange buffers
 constexpr size_t SMEM_BYTES_TM = U * SMEM_UNIT_TM + (size_t)(128 + 128 + 256) * 16 + 16;
 
+// Per-thread twiddles of passes 2 and 3 (they depend on t only), loaded once per kernel: 14 shared-memory loads per
+// transform less, for 56 registers that the TMA kernel has to spare.
+struct TwRegs {
+    cplx w4, w5, w6a, w6b, w7a, w7b, w7c, w7d, w8[2], w9[4];
+    __device__ __forceinline__ void load(const cplx *tw2, const cplx *tw8, const cplx *tw9e, int t) {
+        const int blk = t >> 2;
+        w4 = tw2[blk]; w5 = tw2[16 + blk]; w6a = tw2[32 + blk]; w6b = tw2[48 + blk];
+        w7a = tw2[64 + blk]; w7b = tw2[80 + blk]; w7c = tw2[96 + blk]; w7d = tw2[112 + blk];
+        w8[0] = tw8[t]; w8[1] = tw8[UT + t];
+#pragma unroll
+        for (int g = 0; g < 4; g++) w9[g] = tw9e[g * UT + t];
+    }
+};
+__device__ __forceinline__ void pass2_fwd_r(cplx (&x)[16], const TwRegs &w) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) bf(x[q], x[q + 8], w.w4);
+#pragma unroll
+    for (int q = 0; q < 16; q++) if (!(q & 4)) { if (q & 8) bf_mi(x[q], x[q + 4], w.w5); else bf(x[q], x[q + 4], w.w5); }
+#pragma unroll
+    for (int q = 0; q < 16; q++) if (!(q & 2)) {
+        const cplx ww = (q & 8) ? w.w6b : w.w6a;
+        if (q & 4) bf_mi(x[q], x[q + 2], ww); else bf(x[q], x[q + 2], ww);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q += 2) {
+        const cplx ww = (q >> 2) == 0 ? w.w7a : (q >> 2) == 1 ? w.w7b : (q >> 2) == 2 ? w.w7c : w.w7d;
+        if (q & 2) bf_mi(x[q], x[q + 1], ww); else bf(x[q], x[q + 1], ww);
+    }
+}
+__device__ __forceinline__ void pass2_inv_r(cplx (&x)[16], const TwRegs &w) {
+#pragma unroll
+    for (int q = 0; q < 16; q += 2) {
+        const cplx ww = (q >> 2) == 0 ? w.w7a : (q >> 2) == 1 ? w.w7b : (q >> 2) == 2 ? w.w7c : w.w7d;
+        if (q & 2) bi_mi(x[q], x[q + 1], ww); else bi(x[q], x[q + 1], ww);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) if (!(q & 2)) {
+        const cplx ww = (q & 8) ? w.w6b : w.w6a;
+        if (q & 4) bi_mi(x[q], x[q + 2], ww); else bi(x[q], x[q + 2], ww);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) if (!(q & 4)) { if (q & 8) bi_mi(x[q], x[q + 4], w.w5); else bi(x[q], x[q + 4], w.w5); }
+#pragma unroll
+    for (int q = 0; q < 8; q++) bi(x[q], x[q + 8], w.w4);
+}
+__device__ __forceinline__ void pass3_fwd_r(cplx (&x)[16], const TwRegs &w) {
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const cplx w8 = w.w8[g >> 1], w9 = w.w9[g];
+        if (g & 1) { bf_mi(x[4 * g], x[4 * g + 2], w8); bf_mi(x[4 * g + 1], x[4 * g + 3], w8); }
+        else { bf(x[4 * g], x[4 * g + 2], w8); bf(x[4 * g + 1], x[4 * g + 3], w8); }
+        bf(x[4 * g], x[4 * g + 1], w9);
+        bf_mi(x[4 * g + 2], x[4 * g + 3], w9);
+    }
+}
+__device__ __forceinline__ void pass3_inv_r(cplx (&x)[16], const TwRegs &w) {
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const cplx w8 = w.w8[g >> 1], w9 = w.w9[g];
+        bi(x[4 * g], x[4 * g + 1], w9);
+        bi_mi(x[4 * g + 2], x[4 * g + 3], w9);
+        if (g & 1) { bi_mi(x[4 * g], x[4 * g + 2], w8); bi_mi(x[4 * g + 1], x[4 * g + 3], w8); }
+        else { bi(x[4 * g], x[4 * g + 2], w8); bi(x[4 * g + 1], x[4 * g + 3], w8); }
+    }
+}
+// fft_fwd2 / fft_inv2 with register-resident twiddles
+__device__ __forceinline__ void fft_fwd2r(cplx (&x)[16], cplx *xa, cplx *xc, const TwRegs &w, int t, int unit) {
+    pass1_fwd(x);
+#pragma unroll
+    for (int m = 0; m < 16; m++) xa[t + 68 * m] = x[m];
+    unit_bar(unit);
+    const int blk = t >> 2, o = t & 3;
+#pragma unroll
+    for (int q = 0; q < 16; q++) x[q] = xa[68 * blk + o + 4 * q];
+    pass2_fwd_r(x, w);
+#pragma unroll
+    for (int q = 0; q < 16; q++) xc[68 * blk + o + 4 * q + (q >> 2)] = x[q];
+    unit_bar(unit);
+#pragma unroll
+    for (int e = 0; e < 16; e++) x[e] = xc[17 * t + e];
+    pass3_fwd_r(x, w);
+}
+__device__ __forceinline__ void fft_inv2r(cplx (&x)[16], cplx *xa, cplx *xc, const TwRegs &w, int t, int unit) {
+    pass3_inv_r(x, w);
+#pragma unroll
+    for (int e = 0; e < 16; e++) xa[17 * t + e] = x[e];
+    unit_bar(unit);
+    const int blk = t >> 2, o = t & 3;
+#pragma unroll
+    for (int q = 0; q < 16; q++) x[q] = xa[68 * blk + o + 4 * q + (q >> 2)];
+    pass2_inv_r(x, w);
+#pragma unroll
+    for (int q = 0; q < 16; q++) xc[68 * blk + o + 4 * q] = x[q];
+    unit_bar(unit);
+#pragma unroll
+    for (int m = 0; m < 16; m++) x[m] = xc[t + 68 * m];
+    pass1_inv(x);
+}
+
 // forward transform with double-buffered exchanges; `mid1` / `mid2` run after the exchange reads, i.e. while the
 // pass that follows is still ahead: the caller issues its key prefetches there.
 template <class F1, class F2>
@@ -771,10 +870,11 @@ struct Mono16 {
 // 128 registers per thread, and their latency is hidden by the ring instead of by the scheduler.
 constexpr int RING_BYTES = 5 * H * 16;                                     // 80 KiB of key tiles in flight
 // tile = one polynomial (16 KiB, 5 slots) for the plain kernel, half a polynomial (slots e < 8 / e >= 8 of every thread,
-// 8 KiB, 10 slots) for the block kernel, whose fold then needs 8 + 8 instead of 16 + 16 complex accumulators
+// 8 KiB, 10 slots) for the block kernel, whose fold then needs 8 + 8 instead of 16 + 16 complex accumulators (quarter
+// tiles were measured too: 786 ms against 672 ms at KMS8 block, the barrier traffic doubles)
 template <int ELL> struct TileCfg { static constexpr int TILE = ELL == 1 ? H : H / 2, RING = RING_BYTES / (TILE * 16); };
 constexpr int CTA_TMA = CTA + 128;                                   // 2 consumer warpgroups + 1 producer warpgroup
-constexpr size_t SMEM_BYTES_TMA = U * SMEM_UNIT_TM + (size_t)(128 + 128 + 256) * 16 + (size_t)RING_BYTES + 256;
+constexpr size_t SMEM_BYTES_TMA = U * SMEM_UNIT_TM + (size_t)(128 + 128 + 256) * 16 + (size_t)RING_BYTES + 512;
 
 __device__ __forceinline__ void mb_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
@@ -860,6 +960,17 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
         const bool live = up < gates * (size_t)rows;
         const int gate = live ? (int)(up / rows) : 0, row = live ? (int)(up % rows) : 0;
         const size_t unit_out = a.step_mode ? up : (size_t)gate * a.R + (party == 0 ? 0 : 1 + (size_t)(party - 1) * a.l_lev + row);
+        // the plain kernel keeps its pass-2/3 twiddles in registers; the block kernel has none to spare (measured: +23 % time)
+        TwRegs twr;
+        if constexpr (ELL == 1) twr.load(tw2, tw8, tw9e, t);
+        auto fwd = [&](cplx (&v)[16]) {
+            if constexpr (ELL == 1) fft_fwd2r(v, xa, xc, twr, t, unit_l);
+            else fft_fwd2(v, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+        };
+        auto inv = [&](cplx (&v)[16]) {
+            if constexpr (ELL == 1) fft_inv2r(v, xa, xc, twr, t, unit_l);
+            else fft_inv2(v, xa, xc, tw2, tw8, tw9e, t, unit_l);
+        };
         uint32_t tile_n = 0;                                       // next tile this thread will consume
         auto tile_wait = [&]() -> const cplx * {
             const int slot = tile_n % RING;
@@ -945,7 +1056,7 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                         x[m] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
                     }
                 }
-                fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+                fwd(x);
                 if (ELL == 1) {
                     // both key tiles stay in the ring while the four chunks are processed: key values are read four at a
                     // time right before use instead of occupying 128 registers
@@ -980,13 +1091,14 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                     mb_arrive(&empty[slot_b]);
                     tile_done();
                 } else {
-                    // block: fold the monomials of the block's key bits into the keys (see k_phase1), half of the thread's
-                    // slots at a time: Sum_bit mono_bit * K_bit for e in [8*hf, 8*hf + 8), then the multiply-accumulate
+                    // block: fold the monomials of the block's key bits into the keys (see k_phase1), part of the thread's
+                    // slots at a time: Sum_bit mono_bit * K_bit for e in [EP*part, EP*part + EP), then the multiply-accumulate
+                    constexpr int EP = 16 / HALVES;                 // slots per key tile and thread
 #pragma unroll
-                    for (int hf = 0; hf < 2; hf++) {
-                        cplx kcb[8], kca[8];
+                    for (int hf = 0; hf < HALVES; hf++) {
+                        cplx kcb[EP], kca[EP];
 #pragma unroll
-                        for (int e = 0; e < 8; e++) kcb[e] = kca[e] = make_double2(0.0, 0.0);
+                        for (int e = 0; e < EP; e++) kcb[e] = kca[e] = make_double2(0.0, 0.0);
 #pragma unroll
                         for (int b = 0; b < ELL; b++) {
                             const cplx *kb = tile_wait();
@@ -995,8 +1107,8 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                             const cplx *ka = tile_wait();
                             if (atv[b] != 0) {
 #pragma unroll
-                                for (int eh = 0; eh < 8; eh++) {
-                                    const int e = 8 * hf + eh;
+                                for (int eh = 0; eh < EP; eh++) {
+                                    const int e = EP * hf + eh;
                                     const int b4 = ((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3);
                                     cplx mo = cmul_f(m1v[b], c_e16[(atv[b] * b4) & 15]);
                                     mo.x -= 1.0 / H;
@@ -1008,8 +1120,8 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                             tile_done();
                         }
 #pragma unroll
-                        for (int c2 = 0; c2 < 2; c2++) {
-                            const int c = 2 * hf + c2;
+                        for (int c2 = 0; c2 < EP / 4; c2++) {
+                            const int c = (EP / 4) * hf + c2;
                             cplx zb[4], za[4];
                             if (dg == 0) {
 #pragma unroll
@@ -1062,7 +1174,7 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                         for (int e = 0; e < 16; e++) y[e] = cmul_f(mg.at<false>(e), y[e]);
                     }
                 }
-                fft_inv2(y, xa, xc, tw2, tw8, tw9e, t, unit_l);
+                inv(y);
                 const uint32_t dst = tm + (pz == 0 ? TM_ACC_B : TM_ACC_A);
                 uint32_t v[4][16];
                 tm_ld16(dst, v[0]);
@@ -1105,7 +1217,7 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
                         const uint64_t v0 = ((uint64_t)hi[m] << 32) | lo[m], v1 = ((uint64_t)hi[m + 16] << 32) | lo[m + 16];
                         x[m] = make_double2(__ll2double_rn((long long)v0), __ll2double_rn((long long)((uint64_t)0 - v1)));
                     }
-                    fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+                    fwd(x);
                     if (a.lev_fast) {          // for k_phase2: thread order, and the 1/H of phase 2's inverse transforms (exact)
 #pragma unroll
                         for (int e = 0; e < 16; e++) out[(size_t)pz * H + e * UT + t] = make_double2(x[e].x * (1.0 / H), x[e].y * (1.0 / H));
