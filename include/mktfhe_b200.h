@@ -89,6 +89,8 @@ int mktfhe_finalize_keys(mktfhe_ctx *ctx);
  * batch = 1 is the reference's per-gate call.  Host buffers; H2D and D2H copies are inside the call. */
 int mktfhe_gate_batch(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2,
                       uint32_t *out, size_t batch);
+/* Batches whose scratch (accumulators, RLEV rows: 0.2 MB per gate at KMS2party, 4.6 MB at KMS32party) exceeds the workspace
+ * budget run in chunks inside the call; the budget is min(24 GiB, 40 % of device memory) or $MKTFHE_WORKSPACE_MB. */
 /* Replaces: bootstrapping!(ctxt, scheme) (bootstrapping.jl:4-27) over a batch (out may alias in). */
 int mktfhe_bootstrap_batch(mktfhe_ctx *ctx, const uint32_t *in, uint32_t *out, size_t batch);
 /* Same with ciphertexts already resident in device memory of ctx's device (no copies, asynchronous on

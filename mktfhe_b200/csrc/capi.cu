@@ -417,6 +417,16 @@ int mktfhe_ctx_create(const mktfhe_params *params, int device, mktfhe_ctx **out)
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, MKTFHE_ERR_CUDA, cudaGetErrorString(e)); }
     cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
+    // Workspace budget: batches whose per-gate scratch exceeds it run in chunks.  Default: 24 GiB or 40 % of the device memory,
+    // whichever is smaller; MKTFHE_WORKSPACE_MB overrides (tests use it to force chunking).
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) ctx->mem_budget = std::min(ctx->mem_budget, total_b / 5 * 2);
+        if (const char *e = getenv("MKTFHE_WORKSPACE_MB")) {
+            const long mb = atol(e);
+            if (mb > 0) ctx->mem_budget = (size_t)mb << 20;
+        }
+    }
     *out = ctx;
     return 0;
 }

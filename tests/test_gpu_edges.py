@@ -144,3 +144,28 @@ def test_state_and_argument_errors(gpu_schemes):
     b2, c2 = fresh_inputs(ks, 4, seed=92)
     want = np.array([PLAIN[0](bool(x), bool(y)) for x, y in zip(b1, b2)])
     assert np.array_equal(ks.decrypt_batch(s.gate(0, c1, c2)), want)
+
+
+def test_chunked_batches_match_unchunked(monkeypatch):
+    """A batch larger than the workspace budget runs in chunks inside the call; results must not depend on it."""
+    from mktfhe_b200.scheme import setup
+    ks = keyset("KMS2party")
+    B = 150
+    b1, c1 = fresh_inputs(ks, B, seed=101)
+    b2, c2 = fresh_inputs(ks, B, seed=102)
+    want = np.array([PLAIN[3](bool(x), bool(y)) for x, y in zip(b1, b2)])
+    monkeypatch.setenv("MKTFHE_WORKSPACE_MB", "8")             # ~0.23 MB of scratch per gate -> chunks of ~35 gates
+    small = setup(ks, device=0)
+    monkeypatch.delenv("MKTFHE_WORKSPACE_MB")
+    big = setup(ks, device=0)
+    try:
+        for mode in (MODE_FAST, MODE_STRICT):
+            small.set_mode(mode)
+            big.set_mode(mode)
+            a = small.gate(3, c1, c2)
+            b = big.gate(3, c1, c2)
+            assert np.array_equal(a, b), mode
+            assert np.array_equal(ks.decrypt_batch(a), want)
+    finally:
+        small.close()
+        big.close()
