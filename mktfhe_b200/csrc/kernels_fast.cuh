@@ -874,6 +874,11 @@ constexpr int RING_BYTES = 5 * H * 16;                                     // 80
 // tiles were measured too: 786 ms against 672 ms at KMS8 block, the barrier traffic doubles)
 template <int ELL> struct TileCfg { static constexpr int TILE = ELL == 1 ? H : H / 2, RING = RING_BYTES / (TILE * 16); };
 constexpr int CTA_TMA = CTA + 128;                                   // 2 consumer warpgroups + 1 producer warpgroup
+// `setmaxnreg` only redistributes the registers the CTA was launched with: (launch registers) x warps must cover the
+// re-split, or the last `setmaxnreg.inc` waits forever.  Launch: 12 warps x 168; after: 8 x 232 + 4 x 24.
+constexpr int TMA_LAUNCH_REGS = 168, TMA_CONSUMER_REGS = 232, TMA_PRODUCER_REGS = 24;
+static_assert((CTA / 32) * TMA_CONSUMER_REGS + 4 * TMA_PRODUCER_REGS <= (CTA_TMA / 32) * TMA_LAUNCH_REGS, "setmaxnreg over-subscription");
+static_assert(TMA_LAUNCH_REGS * CTA_TMA <= 65536, "launch registers exceed the register file");
 constexpr size_t SMEM_BYTES_TMA = U * SMEM_UNIT_TM + (size_t)(128 + 128 + 256) * 16 + (size_t)RING_BYTES + 512;
 
 __device__ __forceinline__ void mb_init(uint64_t *bar, int count) {
