@@ -144,3 +144,34 @@ def test_gate_level_argument_errors(gpu_schemes):
         s.wires_read(3, 2)
     s.gate_level(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32))
     s.wires_resize(0)
+
+
+def test_random_netlists_schedule_and_evaluate_consistently():
+    """Random SSA netlists (all opcodes, NOT chains, bare bootstraps): executing the schedule step by step on plaintext bits
+    gives the same wire values as executing the gates in creation order, and every step reads only earlier steps."""
+    rng = np.random.default_rng(2024)
+    plain2 = {0: lambda x, y: not (x and y), 1: lambda x, y: x and y, 2: lambda x, y: x or y,
+              3: lambda x, y: x != y, 4: lambda x, y: x == y, 5: lambda x, y: not (x or y)}
+    for trial in range(40):
+        nin = int(rng.integers(1, 6))
+        c = Circuit(nin)
+        for _ in range(int(rng.integers(1, 40))):
+            kind = rng.random()
+            a, b = int(rng.integers(0, c.n_wires)), int(rng.integers(0, c.n_wires))
+            if kind < 0.15:
+                c.NOT(a)
+            elif kind < 0.22:
+                c.bootstrap(a)
+            else:
+                c.gate(int(rng.integers(0, 6)), a, b)
+        c.set_outputs(list(range(c.n_wires)))
+        bits = rng.integers(0, 2, nin).astype(bool)
+        want = c.evaluate_plain(bits)
+        wires = {i: bool(bits[i]) for i in range(nin)}
+        for ops, s1, s2, dst in c.schedule():
+            new = {}
+            for op, a, b, d in zip(ops.tolist(), s1.tolist(), s2.tolist(), dst.tolist()):
+                assert a in wires and b in wires and d not in wires and d not in new
+                new[d] = (not wires[a]) if op == NOT_OP else wires[a] if op == BOOTSTRAP_OP else bool(plain2[op](wires[a], wires[b]))
+            wires.update(new)
+        assert [wires[w] for w in range(c.n_wires)] == [bool(v) for v in want], trial
