@@ -222,7 +222,7 @@ def main():
         vals = []
         info = None
         for it in range(args.warmup + args.steps):
-            info, _, n = cpu_baseline(ks, c1, c2, budget_s=8.0)
+            info, _, n = cpu_baseline(ks, c1, c2, budget_s=float(os.environ.get("MKTFHE_REF_BUDGET_S", "8.0")))
             if it >= args.warmup:
                 vals.append(info["value"])
         v = float(np.mean(vals)) if vals else info["value"]

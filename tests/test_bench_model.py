@@ -48,3 +48,22 @@ def test_bench_line_carries_the_contract_keys():
     mod = bench_module()
     assert mod.WORKLOADS["kms2"] == ("KMS2party", 4096)                 # BASELINE configs[1]
     assert mod.WORKLOADS["kms32"][1] == 1024 and mod.WORKLOADS["kms8block"][1] == 2048
+
+
+def test_reference_arm_runs_on_cpu_and_prints_one_json_line():
+    """`bench.py --impl reference` needs no GPU: it times the CPU port and prints exactly one JSON line on stdout."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, MKTFHE_REF_BUDGET_S="0.5")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--batch", "16"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "MK-NAND gate bootstraps/sec" and d["unit"] == "gates/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["params"] == "KMS2party"
