@@ -23,7 +23,7 @@ CUDA_LIB = os.path.join(LIBDIR, "libmktfhe_b200.so")
 
 HOST_SRCS = ["host_keygen.cpp"]
 CUDA_SRCS = ["capi.cu"]
-CUDA_DEPS = ["common.cuh", "fft_strict.cuh", "kernels_strict.cuh", "kernels_fast.cuh", "kernels_fast32.cuh", "keyswitch.cuh"]
+CUDA_DEPS = ["common.cuh", "fft_strict.cuh", "kernels_strict.cuh", "kernels_fast.cuh", "kernels_fast_w.cuh", "kernels_fast32.cuh", "keyswitch.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -38,6 +38,7 @@ struct Tables {
     const cplx *t8;        // [2][64]  TW[256 + 4t + g], g = 0, 2
     const cplx *t9;        // [4][64]  TW[512 + 2(4t + g)], g = 0..3
     const cplx *emono;     // [4096] exp(-i*pi*m/2048) / H
+    const cplx *t2w;       // [16][32] pass-2 twiddles of the one-warp transform (kernels_fast_w.cuh)
 };
 
 // ---- butterflies -------------------------------------------------------------------------------------
@@ -890,10 +891,19 @@ __device__ __forceinline__ void mb_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mb_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
+// Bounded spin: a protocol error (a tile nobody releases, a setmaxnreg over-subscription upstream) traps after ~2^26 failed
+// polls (>= 0.5 s; no legitimate wait is longer than a few microseconds) instead of hanging the device until the watchdog.
+__device__ __forceinline__ bool mb_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 "selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mb_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    uint32_t spins = 0;
+    while (!mb_try(bar, parity))
+        if (++spins > (1u << 26)) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -1488,20 +1498,27 @@ __global__ void k_permute_brk(const cplx *__restrict__ in, cplx *__restrict__ ou
 
 }  // namespace fast
 
+#include "kernels_fast_w.cuh"
+
 struct FastKeys {
     std::vector<cplx *> brk;        // per party, FAST layout
     cplx **d_brk = nullptr;
-    cplx *t2 = nullptr, *t8 = nullptr, *t9 = nullptr, *emono = nullptr;
+    cplx *t2 = nullptr, *t8 = nullptr, *t9 = nullptr, *emono = nullptr, *t2w = nullptr;
+    bool brk_w = false;             // brk is in the one-warp kernel's thread order [e < 32][t < 32]
     // phase-2 keys in thread order, scaled by 1/H
     std::vector<cplx *> rlk, pubb;
     cplx **d_rlk = nullptr, **d_pubb = nullptr, *crs = nullptr;
     bool built = false;
 };
 
-static inline bool fast_variant_tma() {
-    static const bool tma = []() { const char *e = getenv("MKTFHE_FAST_KERNEL"); return !e || std::string(e) == "tma"; }();
-    return tma;
+// MKTFHE_FAST_KERNEL = w32 (default: one warp per transform, kernels_fast_w.cuh; KMS_block keeps the tma kernel) | tma | tmem | smem
+static inline const std::string &fast_variant() {
+    static const std::string v = []() { const char *e = getenv("MKTFHE_FAST_KERNEL"); return std::string(e && *e ? e : "w32"); }();
+    return v;
 }
+// the variants that can hand the RLEV rows to k_phase2 in its thread order
+static inline bool fast_variant_tma() { return fast_variant() == "tma" || fast_variant() == "w32"; }
+static inline bool fast_use_w(const mktfhe_params &p) { return fast_variant() == "w32" && p.scheme == MKTFHE_KMS; }
 
 static inline bool fast_supported(const mktfhe_params &p) {
     return p.N == 2048 && (p.scheme == MKTFHE_KMS || (p.scheme == MKTFHE_KMS_BLOCK && p.ell == 3));
@@ -1515,13 +1532,14 @@ static inline void fast_free(FastKeys &f) {
     if (f.t8) cudaFree(f.t8);
     if (f.t9) cudaFree(f.t9);
     if (f.emono) cudaFree(f.emono);
+    if (f.t2w) cudaFree(f.t2w);
     for (auto &q : f.rlk) if (q) cudaFree(q);
     for (auto &q : f.pubb) if (q) cudaFree(q);
     f.rlk.clear(); f.pubb.clear();
     if (f.d_rlk) cudaFree(f.d_rlk);
     if (f.d_pubb) cudaFree(f.d_pubb);
     if (f.crs) cudaFree(f.crs);
-    f.d_brk = nullptr; f.t2 = f.t8 = f.t9 = f.emono = nullptr; f.d_rlk = f.d_pubb = nullptr; f.crs = nullptr; f.built = false;
+    f.d_brk = nullptr; f.t2 = f.t8 = f.t9 = f.emono = f.t2w = nullptr; f.brk_w = false; f.d_rlk = f.d_pubb = nullptr; f.crs = nullptr; f.built = false;
 }
 
 #define FCK(call)                                                                        \
@@ -1563,6 +1581,23 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
     }
     for (int j = 0; j < 16; j++) { const __float128 ang = pi * j / 8; e16[j] = make_double2((double)cosq(ang), (double)-sinq(ang)); }
     for (int i = 1; i < 16; i++) tw1[i] = tw[i];
+    {   // one-warp transform (kernels_fast_w.cuh): stages 1..5 in the constant bank, stages 6..10 per thread [16][32]
+        std::vector<cplx> tw1w(32, make_double2(0.0, 0.0)), e32(32), t2w(512);
+        for (int i = 1; i < 32; i++) tw1w[i] = tw[i];
+        for (int j = 0; j < 32; j++) { const __float128 ang = pi * j / 16; e32[j] = make_double2((double)cosq(ang), (double)-sinq(ang)); }
+        for (int t = 0; t < 32; t++) {
+            t2w[t] = tw[32 + t];
+            t2w[32 + t] = tw[64 + 2 * t];
+            for (int g = 0; g < 2; g++) t2w[(2 + g) * 32 + t] = tw[128 + 4 * t + 2 * g];
+            for (int g = 0; g < 4; g++) t2w[(4 + g) * 32 + t] = tw[256 + 8 * t + 2 * g];
+            for (int g = 0; g < 8; g++) t2w[(8 + g) * 32 + t] = tw[512 + 16 * t + 2 * g];
+        }
+        FCK(cudaMalloc(&f.t2w, sizeof(cplx) * 512));
+        FCK(cudaMemcpy(f.t2w, t2w.data(), sizeof(cplx) * 512, cudaMemcpyHostToDevice));
+        FCK(cudaMemcpyToSymbol(fastw::c_tw1w, tw1w.data(), sizeof(cplx) * 32));
+        FCK(cudaMemcpyToSymbol(fastw::c_e32, e32.data(), sizeof(cplx) * 32));
+        FCK(cudaFuncSetAttribute(fastw::k_phase1_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fastw::SMEM_BYTES_W));
+    }
     FCK(cudaMalloc(&f.t2, sizeof(cplx) * 128));
     FCK(cudaMalloc(&f.t8, sizeof(cplx) * 128));
     FCK(cudaMalloc(&f.t9, sizeof(cplx) * 256));
@@ -1577,9 +1612,11 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
     f.brk.assign(brk_ref.size(), nullptr);
     for (size_t i = 0; i < brk_ref.size(); i++) {
         FCK(cudaMalloc(&f.brk[i], polys * H * sizeof(cplx)));
-        k_permute_brk<<<(unsigned)((polys * H + 255) / 256), 256, 0, stream>>>(brk_ref[i], f.brk[i], polys);
+        if (fast_use_w(p)) fastw::k_permute_brk_w<<<(unsigned)((polys * H + 255) / 256), 256, 0, stream>>>(brk_ref[i], f.brk[i], polys);
+        else k_permute_brk<<<(unsigned)((polys * H + 255) / 256), 256, 0, stream>>>(brk_ref[i], f.brk[i], polys);
         FCK(cudaGetLastError());
     }
+    f.brk_w = fast_use_w(p);
     FCK(cudaMalloc(&f.d_brk, sizeof(cplx *) * f.brk.size()));
     FCK(cudaMemcpy(f.d_brk, f.brk.data(), sizeof(cplx *) * f.brk.size(), cudaMemcpyHostToDevice));
     FCK(cudaFuncSetAttribute(k_phase1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -1614,13 +1651,22 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
 static inline int fast_launch(FastKeys &f, const mktfhe_params &p, fast::Args a, cudaStream_t stream, int *launches, std::string &err) {
     using namespace fast;
     if (!f.built) { err = "FAST keys not built"; return -3; }
-    a.brk = f.d_brk; a.tb = Tables{f.t2, f.t8, f.t9, f.emono};
+    a.brk = f.d_brk; a.tb = Tables{f.t2, f.t8, f.t9, f.emono, f.t2w};
     a.n = p.n; a.k = p.k; a.l = p.l_gsw; a.logB = p.logB_gsw; a.l_lev = p.l_lev; a.logB_lev = p.logB_lev;
     a.R = 1 + (p.k - 1) * p.l_lev; a.lwe_words = (int)mktfhe_lwe_words(&p);
     const unsigned grid = (unsigned)((a.units + U - 1) / U);
     a.d = p.d;
-    static const std::string variant = []() { const char *e = getenv("MKTFHE_FAST_KERNEL"); return std::string(e ? e : "tma"); }();      // tma | tmem | smem
-    if (variant == "tma") {
+    const std::string variant = fast_use_w(p) ? "w32" : (fast_variant() == "w32" ? "tma" : fast_variant());      // w32 | tma | tmem | smem
+    if (variant == "w32") {
+        if (!f.brk_w) { err = "FAST keys are not in the one-warp kernel's order"; return -3; }
+        size_t ctas;
+        if (a.step_mode) ctas = (a.units + fastw::WU - 1) / fastw::WU;
+        else {
+            const size_t gates = a.units / a.R;
+            ctas = (gates + fastw::WU - 1) / fastw::WU + (size_t)(p.k - 1) * ((gates * p.l_lev + fastw::WU - 1) / fastw::WU);
+        }
+        fastw::k_phase1_w<<<(unsigned)ctas, fastw::CTA_W, fastw::SMEM_BYTES_W, stream>>>(a);
+    } else if (variant == "tma") {
         // CTAs are grouped by party (one key stream per CTA): ceil(gates/U) for party 0 plus ceil(gates*l_lev/U) per other party
         size_t ctas;
         if (a.step_mode) ctas = (a.units + U - 1) / U;
@@ -1666,7 +1712,7 @@ static inline int fast_phase2(FastKeys &f, const mktfhe_params &p, const uint32_
     using namespace fast;
     if (!f.built) { err = "FAST keys not built"; return -3; }
     P2Args a{};
-    a.tilde = tilde; a.lev = lev; a.rlk = f.d_rlk; a.pubb = f.d_pubb; a.crs = f.crs; a.tb = Tables{f.t2, f.t8, f.t9, f.emono};
+    a.tilde = tilde; a.lev = lev; a.rlk = f.d_rlk; a.pubb = f.d_pubb; a.crs = f.crs; a.tb = Tables{f.t2, f.t8, f.t9, f.emono, f.t2w};
     a.acc = acc; a.tx = tx; a.ty = ty;
     a.k = p.k; a.l_lev = p.l_lev; a.logB_lev = p.logB_lev; a.l_uni = p.l_uni; a.logB_uni = p.logB_uni;
     a.R = 1 + (p.k - 1) * p.l_lev; a.lwe_words = (int)mktfhe_lwe_words(&p); a.gates = gates;

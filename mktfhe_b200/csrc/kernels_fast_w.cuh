@@ -1,0 +1,440 @@
+// kernels_fast_w.cuh -- FAST-mode KMS phase 1, "one warp per transform" variant (production default for ELL = 1).
+//
+// What it computes: /root/reference/src/tfhe/bootstrapping.jl:389-443 (phase_1 of KMS), exactly like
+// fast::k_phase1_tma (kernels_fast.cuh) -- same integer stages, same twist-free product-tree transform, same slot
+// order -- with a different mapping onto the SM:
+//
+//   * A 1024-point transform belongs to ONE warp: 32 threads x 32 points, passes of 5 + 5 stages in registers and a
+//     single warp-local transposition through shared memory in between (__syncwarp, no block barrier).  Against the
+//     64-thread x 16-point mapping (4 + 4 + 2 stages, two exchanges, four named barriers per transform) this halves the
+//     shared-memory exchange traffic -- the L1/shared data pipe was 59 % busy next to an FP64 pipe at 58 % -- removes
+//     every barrier from the transforms and doubles the independent butterflies per stage (32 chains).
+//   * A unit = one (gate, party, RLEV row) still owns one TMEM lane quadrant (64 KiB: RLWE accumulator + RGSW
+//     accumulators), shared by TWO warps q and q + 4 (same quadrant, same scheduler).  The 2l gadget digits of a step
+//     alternate between them: warp A transforms digits 0, 2, 4, ..., warp B digits 1, 3, 5, ...; each multiplies its
+//     spectrum into the shared RGSW accumulators when it holds the token (named-barrier arrive / sync pairs, strictly
+//     alternating A, B, A, ...), so the accumulation order over the digits is the sequential one.  Then A inverse-
+//     transforms the .b output and B the .a output, each updates its half of the RLWE accumulator, and one 64-thread
+//     barrier closes the step.  Per step and unit: 2l token hand-offs + 1 barrier instead of 32 blocking barriers.
+//   * Bootstrapping-key tiles arrive once per CTA through the same cp.async.bulk + mbarrier ring as before; a tile is
+//     consumed by the one warp per unit that owns its digit (one elected lane per warp releases the slot).
+//
+// Index math of the transform is modelled and checked against the oracle in tools/models/fft32_model.py.
+#pragma once
+#include "kernels_fast.cuh"
+
+namespace fastw {
+
+using fast::H; using fast::N;
+using fast::bf; using fast::bf_mi; using fast::bi; using fast::bi_mi;
+using fast::tm_ld16; using fast::tm_st16; using fast::tm_wait_ld; using fast::tm_wait_st; using fast::tm_pin16; using fast::tm_st_c4;
+using fast::mb_init; using fast::mb_expect_tx; using fast::mb_arrive; using fast::mb_wait; using fast::bulk_g2s; using fast::d2torus;
+
+constexpr int WU = 4;                       // units per CTA = TMEM lane quadrants
+constexpr int NCW = 2 * WU;                 // consumer warps
+constexpr int CTA_W = NCW * 32 + 128;       // + producer warpgroup (setmaxnreg works on warpgroups)
+constexpr int XBW = H + 32;                 // exchange buffer: element n at n + (n >> 5)
+constexpr int RINGW = 5;                    // key tiles (16 KiB polynomials) in flight
+constexpr int W_LAUNCH_REGS = 168, W_CONSUMER_REGS = 232, W_PRODUCER_REGS = 24;
+static_assert(NCW * W_CONSUMER_REGS + 4 * W_PRODUCER_REGS <= (CTA_W / 32) * W_LAUNCH_REGS, "setmaxnreg over-subscription");
+constexpr size_t SMEM_BYTES_W = ((size_t)NCW * XBW + 512 + (size_t)RINGW * H) * 16 + 2 * RINGW * 8 + 16;
+static_assert(SMEM_BYTES_W <= 232448, "shared memory budget");
+
+__constant__ double2 c_tw1w[32];     // TW[1..31]: stages 1..5 (index 2^s + node), entry 0 unused
+__constant__ double2 c_e32[32];      // exp(-i*pi*j/16)
+
+// TMEM columns of a lane: RGSW accumulators (32 complex each), RLWE accumulator (coefficient t + 32m at 4m, 4m+1 and
+// coefficient t + 32m + H at 4m+2, 4m+3 of its half)
+constexpr uint32_t TMW_TACC_B = 0, TMW_TACC_A = 128, TMW_ACC_B = 256, TMW_ACC_A = 384;
+
+// ---- transform: x (layout A: element m = point t + 32m) <-> x (layout C: element e = slot 32t + e) -----------------
+__device__ __forceinline__ void pass1_fwd(cplx (&x)[32]) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+#pragma unroll
+        for (int m = 0; m < 32; m++) {
+            const int half = 16 >> s;
+            if (m & half) continue;
+            const int node = m >> (5 - s);
+            if (node & 1) bf_mi(x[m], x[m + half], c_tw1w[(1 << s) + (node & ~1)]);
+            else bf(x[m], x[m + half], c_tw1w[(1 << s) + node]);
+        }
+    }
+}
+__device__ __forceinline__ void pass1_inv(cplx (&x)[32]) {
+#pragma unroll
+    for (int s = 4; s >= 0; s--) {
+#pragma unroll
+        for (int m = 0; m < 32; m++) {
+            const int half = 16 >> s;
+            if (m & half) continue;
+            const int node = m >> (5 - s);
+            if (node & 1) bi_mi(x[m], x[m + half], c_tw1w[(1 << s) + (node & ~1)]);
+            else bi(x[m], x[m + half], c_tw1w[(1 << s) + node]);
+        }
+    }
+}
+// stages 6..10 on the thread's 32 contiguous slots; tw = shared table [16][32] + lane:
+//   row 0: TW[32 + t]; row 1: TW[64 + 2t]; rows 2+g: TW[128 + 4t + 2g]; rows 4+g: TW[256 + 8t + 2g]; rows 8+g: TW[512 + 16t + 2g]
+__device__ __forceinline__ void pass2_fwd(cplx (&x)[32], const cplx *__restrict__ tw) {
+    {
+        const cplx w = tw[0];
+#pragma unroll
+        for (int e = 0; e < 16; e++) bf(x[e], x[e + 16], w);
+    }
+#pragma unroll
+    for (int s = 6; s < 10; s++) {
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            const int half = 16 >> (s - 5);
+            if (e & half) continue;
+            const int sub = e >> (10 - s);
+            const cplx w = tw[((1 << (s - 6)) + (sub >> 1)) * 32];
+            if (sub & 1) bf_mi(x[e], x[e + half], w); else bf(x[e], x[e + half], w);
+        }
+    }
+}
+__device__ __forceinline__ void pass2_inv(cplx (&x)[32], const cplx *__restrict__ tw) {
+#pragma unroll
+    for (int s = 9; s >= 6; s--) {
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            const int half = 16 >> (s - 5);
+            if (e & half) continue;
+            const int sub = e >> (10 - s);
+            const cplx w = tw[((1 << (s - 6)) + (sub >> 1)) * 32];
+            if (sub & 1) bi_mi(x[e], x[e + half], w); else bi(x[e], x[e + half], w);
+        }
+    }
+    {
+        const cplx w = tw[0];
+#pragma unroll
+        for (int e = 0; e < 16; e++) bi(x[e], x[e + 16], w);
+    }
+}
+// xb: this warp's exchange buffer; element n lives at n + (n >> 5): writes (lane-consecutive) and reads (stride 33) are
+// conflict-free for 16-byte accesses
+__device__ __forceinline__ void fft_fwd(cplx (&x)[32], cplx *xb, const cplx *tw, int t) {
+    pass1_fwd(x);
+    __syncwarp();                                       // earlier readers of xb are done
+#pragma unroll
+    for (int m = 0; m < 32; m++) xb[t + 33 * m] = x[m];
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; e++) x[e] = xb[33 * t + e];
+    pass2_fwd(x, tw);
+}
+__device__ __forceinline__ void fft_inv(cplx (&x)[32], cplx *xb, const cplx *tw, int t) {
+    pass2_inv(x, tw);
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; e++) xb[33 * t + e] = x[e];
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 32; m++) x[m] = xb[t + 33 * m];
+    pass1_inv(x);
+}
+
+__device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0, 64;" :: "r"(id) : "memory"); }
+__device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ cplx unpack_c(const uint32_t (&v)[16], int i) {
+    return make_double2(__hiloint2double((int)v[4 * i + 1], (int)v[4 * i]), __hiloint2double((int)v[4 * i + 3], (int)v[4 * i + 2]));
+}
+
+__global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, t = tid & 31;
+    cplx *xb_all = reinterpret_cast<cplx *>(smem_raw);
+    cplx *tw2s = xb_all + (size_t)NCW * XBW;
+    cplx *ring = tw2s + 512;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)RINGW * H), *empty = full + RINGW;
+    uint32_t *tm_base_s = reinterpret_cast<uint32_t *>(empty + RINGW);
+    for (int i = tid; i < 512; i += CTA_W) tw2s[i] = a.tb.t2w[i];
+    if (tid == 0) {
+        for (int s = 0; s < RINGW; s++) { mb_init(&full[s], 1); mb_init(&empty[s], WU); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"((uint32_t)__cvta_generic_to_shared(tm_base_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tm_fence_before();
+    __syncthreads();
+    tm_fence_after();
+
+    // ---- CTA -> (party, units): party 0 has one RLEV row per gate, the others l_lev (bootstrapping.jl:400)
+    int party, rows;
+    size_t u0, gates;
+    if (!a.step_mode) {
+        gates = a.units / a.R;
+        const size_t ctas0 = (gates + WU - 1) / WU, ctasp = (gates * a.l_lev + WU - 1) / WU;
+        if (blockIdx.x < ctas0) { party = 0; rows = 1; u0 = (size_t)blockIdx.x * WU; }
+        else { party = 1 + (int)((blockIdx.x - ctas0) / ctasp); rows = a.l_lev; u0 = ((blockIdx.x - ctas0) % ctasp) * WU; }
+    } else { gates = a.units; party = a.step_party; rows = 1; u0 = (size_t)blockIdx.x * WU; }
+    const int l = a.l;
+    const size_t per_idx = (size_t)4 * l * H;
+    const int nsteps = a.step_mode ? 1 : a.n;
+    const cplx *brk = a.brk[party];
+    const uint32_t ntiles = (uint32_t)nsteps * 2 * l * 2;
+
+    if (warp >= NCW) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        // ---- producer: tile n = (step * 2l + dg) * 2 + comp, one 16 KiB polynomial in thread order [e][t]
+        if (tid == NCW * 32) {
+            for (uint32_t n = 0; n < ntiles; n++) {
+                const int slot = n % RINGW;
+                if (n >= RINGW) mb_wait(&empty[slot], ((n / RINGW) - 1) & 1);
+                const uint32_t within = n % (uint32_t)(4 * l), step = n / (uint32_t)(4 * l);
+                const int idx = a.step_mode ? a.step_idx : (int)step;
+                mb_expect_tx(&full[slot], H * 16);
+                bulk_g2s(ring + (size_t)slot * H, brk + (size_t)idx * per_idx + (size_t)within * H, H * 16, &full[slot]);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        // ---- consumers: unit q = TMEM lane quadrant, role w (0: even digits and the .b output, 1: odd digits and .a)
+        const int q = warp & 3, w = warp >> 2;
+        const int BAR_STEP = 1 + q, BAR_AB = 5 + q, BAR_BA = 9 + q;
+        const uint32_t tm = *tm_base_s + ((uint32_t)(32 * q) << 16);
+        cplx *xb = xb_all + (size_t)warp * XBW;
+        const cplx *tw = tw2s + t;
+        const size_t up = u0 + q;                                  // unit index inside the party
+        const bool live = up < gates * (size_t)rows;
+        const int gate = live ? (int)(up / rows) : 0, row = live ? (int)(up % rows) : 0;
+        const size_t unit_out = a.step_mode ? up : (size_t)gate * a.R + (party == 0 ? 0 : 1 + (size_t)(party - 1) * a.l_lev + row);
+        const uint32_t tm_acc = tm + (w == 0 ? TMW_ACC_B : TMW_ACC_A), tm_tacc = tm + (w == 0 ? TMW_TACC_B : TMW_TACC_A);
+
+        if (live) {                                                // each warp initialises its half of the RLWE accumulator
+            if (!a.step_mode) {
+                uint32_t z[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) z[i] = 0u;
+                const uint64_t gv = (t == 0 && w == 0) ? (uint64_t)1 << (64 - (row + 1) * a.logB_lev) : 0;   // bootstrapping.jl:402-408
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    z[0] = c == 0 ? (uint32_t)gv : 0u;
+                    z[1] = c == 0 ? (uint32_t)(gv >> 32) : 0u;
+                    tm_st16(tm_acc + 16 * c, z);
+                }
+            } else {
+                const uint64_t *src = a.acc_io + up * 2 * N + (size_t)w * N;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint64_t c0 = src[t + 32 * (4 * c + i)], c1 = src[t + 32 * (4 * c + i) + H];
+                        v[4 * i] = (uint32_t)c0; v[4 * i + 1] = (uint32_t)(c0 >> 32); v[4 * i + 2] = (uint32_t)c1; v[4 * i + 3] = (uint32_t)(c1 >> 32);
+                    }
+                    tm_st16(tm_acc + 16 * c, v);
+                }
+            }
+            tm_wait_st();
+            tm_fence_before();
+            nb_sync(BAR_STEP);
+            tm_fence_after();
+        }
+        const int logB = a.logB;
+        const int bit = 64 - l * logB;
+        // divbits rounding + balanced-digit carry chain in one 64-bit add (see kernels_fast.cuh)
+        uint64_t cadd = (uint64_t)1 << (bit - 1);
+        for (int j = 0; j < l; j++) cadd += (uint64_t)1 << (bit + j * logB + logB - 1);
+        const uint32_t mask = (1u << logB) - 1;
+        const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));
+        const uint32_t *at_src = a.step_mode ? a.tilde + up : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
+        const int brv5t = (int)(__brev((unsigned)t) >> 27);
+
+        for (int step = 0; step < nsteps; step++) {
+            const uint32_t at = live ? at_src[a.step_mode ? 0 : step] : 0u;
+            const uint32_t tile0 = (uint32_t)step * 4 * l;          // first tile of this step
+            if (at == 0) {                                          // :413 / dead unit: keep the ring moving, compute nothing
+                for (int j = 0; j < l; j++)
+#pragma unroll
+                    for (int comp = 0; comp < 2; comp++) {
+                        const uint32_t n = tile0 + (uint32_t)(2 * j + w) * 2 + comp;
+                        mb_wait(&full[n % RINGW], (n / RINGW) & 1);
+                        __syncwarp();
+                        if (t == 0) mb_arrive(&empty[n % RINGW]);
+                    }
+                continue;
+            }
+            const cplx m1 = __ldg(&a.tb.emono[((4 * brv5t + 1) * at) & 4095]);
+
+            for (int j = 0; j < l; j++) {
+                const int dg = 2 * j + w;
+                const uint32_t src = tm + (dg < l ? TMW_ACC_B : TMW_ACC_A);
+                const int sh = bit + (l - 1 - (dg < l ? dg : dg - l)) * logB;
+                cplx x[32];
+#pragma unroll
+                for (int hb = 0; hb < 2; hb++) {                     // gadget digit of 64 coefficients -> 32 complex points
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) tm_ld16(src + 64 * hb + 16 * c, v[c]);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        tm_pin16(v[c]);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint64_t v0 = (((uint64_t)v[c][4 * i + 1] << 32) | v[c][4 * i]) + cadd;
+                            const uint64_t v1 = (((uint64_t)v[c][4 * i + 3] << 32) | v[c][4 * i + 2]) + cadd;
+                            const uint32_t f0 = (uint32_t)(v0 >> sh) & mask, f1 = (uint32_t)(v1 >> sh) & mask;
+                            // signed(d_j) - im*signed(d_{j+H}); 2^52 + field is exact in the double's mantissa
+                            x[16 * hb + 4 * c + i] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
+                        }
+                    }
+                }
+                fft_fwd(x, xb, tw, t);
+                const uint32_t nb = tile0 + (uint32_t)dg * 2, na = nb + 1;
+                mb_wait(&full[nb % RINGW], (nb / RINGW) & 1);
+                mb_wait(&full[na % RINGW], (na / RINGW) & 1);
+                const cplx *kb = ring + (size_t)(nb % RINGW) * H + t, *ka = ring + (size_t)(na % RINGW) * H + t;
+                if (dg != 0) {                                      // token: the previous digit's products are in TMEM
+                    nb_sync(w == 0 ? BAR_BA : BAR_AB);
+                    tm_fence_after();
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    cplx zb[4], za[4], kcb[4], kca[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { kcb[i] = kb[(4 * c + i) * 32]; kca[i] = ka[(4 * c + i) * 32]; }
+                    if (dg == 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { zb[i] = cmul_f(x[4 * c + i], kcb[i]); za[i] = cmul_f(x[4 * c + i], kca[i]); }
+                    } else {
+                        uint32_t vb[16], va[16];
+                        tm_ld16(tm + TMW_TACC_B + 16 * c, vb);
+                        tm_ld16(tm + TMW_TACC_A + 16 * c, va);
+                        tm_wait_ld();
+                        tm_pin16(vb); tm_pin16(va);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            zb[i] = cmac_f(unpack_c(vb, i), x[4 * c + i], kcb[i]);
+                            za[i] = cmac_f(unpack_c(va, i), x[4 * c + i], kca[i]);
+                        }
+                    }
+                    tm_st_c4(tm + TMW_TACC_B + 16 * c, zb);
+                    tm_st_c4(tm + TMW_TACC_A + 16 * c, za);
+                }
+                tm_wait_st();
+                tm_fence_before();
+                nb_arrive(w == 0 ? BAR_AB : BAR_BA);                // pass the token
+                __syncwarp();
+                if (t == 0) { mb_arrive(&empty[nb % RINGW]); mb_arrive(&empty[na % RINGW]); }
+            }
+            if (w == 0) {                                           // B's last product closes the sums
+                nb_sync(BAR_BA);
+                tm_fence_after();
+            }
+            // this warp's output: (x (X^a - 1)/H) -> inverse transform -> round -> acc +=
+            {
+                cplx y[32];
+#pragma unroll
+                for (int hb = 0; hb < 2; hb++) {
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) tm_ld16(tm_tacc + 64 * hb + 16 * c, v[c]);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        tm_pin16(v[c]);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) y[16 * hb + 4 * c + i] = unpack_c(v[c], i);
+                    }
+                }
+                // slot 32t + e evaluates at exp(-i*pi*(4*brv10(n)+1)/N), brv10(n) = 32*brv5(e) + brv5(t)
+#pragma unroll
+                for (int e = 0; e < 32; e++) {
+                    const int b5 = ((e & 1) << 4) | ((e & 2) << 2) | (e & 4) | ((e & 8) >> 2) | ((e & 16) >> 4);
+                    cplx mo = cmul_f(m1, c_e32[(at * b5) & 31]);
+                    mo.x -= 1.0 / H;
+                    y[e] = cmul_f(mo, y[e]);
+                }
+                fft_inv(y, xb, tw, t);
+                uint32_t v[2][16];
+                tm_ld16(tm_acc, v[0]);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    tm_wait_ld();
+                    tm_pin16(v[c & 1]);
+                    if (c < 7) tm_ld16(tm_acc + 16 * (c + 1), v[(c + 1) & 1]);      // next chunk in flight during the rounding
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int m = 4 * c + i;
+                        const uint64_t w0 = (((uint64_t)v[c & 1][4 * i + 1] << 32) | v[c & 1][4 * i]) + d2torus(y[m].x);
+                        const uint64_t w1 = (((uint64_t)v[c & 1][4 * i + 3] << 32) | v[c & 1][4 * i + 2]) + d2torus(-y[m].y);
+                        v[c & 1][4 * i] = (uint32_t)w0; v[c & 1][4 * i + 1] = (uint32_t)(w0 >> 32);
+                        v[c & 1][4 * i + 2] = (uint32_t)w1; v[c & 1][4 * i + 3] = (uint32_t)(w1 >> 32);
+                    }
+                    tm_st16(tm_acc + 16 * c, v[c & 1]);
+                }
+                tm_wait_st();
+            }
+            tm_fence_before();
+            nb_sync(BAR_STEP);                                      // both halves of the accumulator are updated
+            tm_fence_after();
+        }
+
+        if (live) {
+            if (!a.step_mode) {            // fftto!(tacc, acc): bootstrapping.jl:441 -- full-width coefficients, warp A .b, warp B .a
+                cplx *out = a.lev_out + unit_out * 2 * H + (size_t)w * H;
+                cplx x[32];
+#pragma unroll
+                for (int hb = 0; hb < 2; hb++) {
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) tm_ld16(tm_acc + 64 * hb + 16 * c, v[c]);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        tm_pin16(v[c]);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint64_t v0 = ((uint64_t)v[c][4 * i + 1] << 32) | v[c][4 * i], v1 = ((uint64_t)v[c][4 * i + 3] << 32) | v[c][4 * i + 2];
+                            x[16 * hb + 4 * c + i] = make_double2(__ll2double_rn((long long)v0), __ll2double_rn((long long)((uint64_t)0 - v1)));
+                        }
+                    }
+                }
+                fft_fwd(x, xb, tw, t);
+                if (a.lev_fast) {          // for k_phase2: its thread order [n & 15][n >> 4] and the 1/H of its inverse transforms (exact)
+#pragma unroll
+                    for (int e = 0; e < 32; e++) out[(e & 15) * 64 + 2 * t + (e >> 4)] = make_double2(x[e].x * (1.0 / H), x[e].y * (1.0 / H));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e++) out[32 * t + e] = x[e];
+                }
+            } else {
+                uint64_t *dst = a.acc_io + up * 2 * N + (size_t)w * N;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t v[16];
+                    tm_ld16(tm_acc + 16 * c, v);
+                    tm_wait_ld();
+                    tm_pin16(v);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        dst[t + 32 * (4 * c + i)] = ((uint64_t)v[4 * i + 1] << 32) | v[4 * i];
+                        dst[t + 32 * (4 * c + i) + H] = ((uint64_t)v[4 * i + 3] << 32) | v[4 * i + 2];
+                    }
+                }
+            }
+        }
+    }
+    tm_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tm_base_s));
+}
+
+// reference slot order [poly][32t + e] -> thread order [poly][e][t]
+__global__ void k_permute_brk_w(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= polys * H) return;
+    const size_t p = i / H;
+    const int r = (int)(i % H), e = r / 32, t = r % 32;
+    out[i] = in[p * H + 32 * t + e];
+}
+
+}  // namespace fastw
