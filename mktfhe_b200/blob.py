@@ -6,7 +6,7 @@ conversion, and a blob written on one machine is the upload input on another.
 
     offset 0      magic  b"MKTFHEB2"
            8      uint32 version (1), uint32 header bytes (little endian)
-           16     JSON header, UTF-8: {"kind": "keys" | "ciphertexts", "params": {...}, "seed": ..,
+           16     JSON header, UTF-8: {"kind": "keys" | "ciphertexts", "params": {...}, "seed": .. (null unless include_secret),
                   "arrays": [{"name", "dtype", "shape", "offset", "nbytes", "sha256"}, ...]}
            ...    each array at a 4096-byte aligned offset, C order, little endian
 
@@ -93,7 +93,9 @@ def save_keys(path: str, keys: KeySet, include_secret: bool = False) -> int:
         for f in _EVAL + (_SECRET if include_secret else ()):
             if q.get(f) is not None:
                 arrays.append((f"p{i}.{f}", q[f]))
-    return _write(path, "keys", p, keys.seed, arrays)
+    # The seed regenerates every secret (an int seed is a test convenience): it goes into the file only together with the secrets.
+    seed = keys.seed if (include_secret and isinstance(keys.seed, int)) else None
+    return _write(path, "keys", p, seed, arrays)
 
 
 class LoadedKeys(KeySet):

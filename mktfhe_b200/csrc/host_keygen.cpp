@@ -36,10 +36,21 @@ struct ChaCha20 {
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         return z ^ (z >> 31);
     }
-    ChaCha20(uint64_t seed, uint64_t stream) {
+    // The 256-bit ChaCha key.  Production callers pass 32 bytes from the OS CSPRNG (one independent key per party, per
+    // CRS and per encryption, like the reference's unseeded ChaCha20Stream() calls: sampler.jl:2-34, lwe.jl:13).  A 64-bit
+    // integer seed expands to a key through splitmix64: reproducible streams for tests, benchmarks and golden vectors only.
+    struct Key {
+        uint32_t k[8];
+        static Key from_seed(uint64_t seed) {
+            Key r; uint64_t x = seed;
+            for (int i = 0; i < 4; i++) { uint64_t kx = splitmix(x); r.k[2 * i] = (uint32_t)kx; r.k[2 * i + 1] = (uint32_t)(kx >> 32); }
+            return r;
+        }
+        static Key from_bytes(const uint8_t *b) { Key r; memcpy(r.k, b, 32); return r; }
+    };
+    ChaCha20(const Key &key, uint64_t stream) {
         st[0] = 0x61707865; st[1] = 0x3320646e; st[2] = 0x79622d32; st[3] = 0x6b206574;
-        uint64_t x = seed;
-        for (int i = 0; i < 4; i++) { uint64_t kx = splitmix(x); st[4 + 2 * i] = (uint32_t)kx; st[5 + 2 * i] = (uint32_t)(kx >> 32); }
+        for (int i = 0; i < 8; i++) st[4 + i] = key.k[i];
         st[12] = 0; st[13] = 0;
         st[14] = (uint32_t)stream; st[15] = (uint32_t)(stream >> 32);
     }
@@ -236,7 +247,7 @@ void lwe_sample(ChaCha20 &rng, const int8_t *key, int n, double sigma, uint32_t 
 }
 
 template <class T>
-int party_keygen_impl(const mktfhe_params *p, uint64_t seed, int party, const T *crs, uint32_t *lwekey_out, T *ringkey_out,
+int party_keygen_impl(const mktfhe_params *p, const ChaCha20::Key &seed, int party, const T *crs, uint32_t *lwekey_out, T *ringkey_out,
                       double *brk, double *rlk, double *pubb, uint32_t *ksk, int nthreads) {
     const int N = p->N, H = N / 2, n = p->n;
     const Tables &tb = tables_for(N);
@@ -318,7 +329,7 @@ int party_keygen_impl(const mktfhe_params *p, uint64_t seed, int party, const T 
     return 0;
 }
 
-template <class T> int crs_impl(const mktfhe_params *p, uint64_t seed, T *coeff, double *fftout) {
+template <class T> int crs_impl(const mktfhe_params *p, const ChaCha20::Key &seed, T *coeff, double *fftout) {
     const int N = p->N, H = N / 2;
     const Tables &tb = tables_for(N);
     ChaCha20 rng(seed, stream_id(S_CRS, 0, 0));
@@ -333,31 +344,70 @@ inline uint32_t mu_of(int m) { return ((uint32_t)(2 * (m ? 1 : 0) - 1)) << 29; }
 
 extern "C" {
 
-int mktfhe_host_crs(const mktfhe_params *p, uint64_t seed, void *crs_coeff, double *crs_fft) {
+static int crs_any(const mktfhe_params *p, const ChaCha20::Key &seed, void *crs_coeff, double *crs_fft) {
     if (p->scheme != MKTFHE_CCS && p->scheme != MKTFHE_KMS && p->scheme != MKTFHE_KMS_BLOCK) return -1;
     return mktfhe_torus_bits(p) == 64 ? crs_impl<uint64_t>(p, seed, (uint64_t *)crs_coeff, crs_fft)
                                       : crs_impl<uint32_t>(p, seed, (uint32_t *)crs_coeff, crs_fft);
 }
+int mktfhe_host_crs(const mktfhe_params *p, uint64_t seed, void *crs_coeff, double *crs_fft) {
+    return crs_any(p, ChaCha20::Key::from_seed(seed), crs_coeff, crs_fft);
+}
+int mktfhe_host_crs_key(const mktfhe_params *p, const uint8_t *key32, void *crs_coeff, double *crs_fft) {
+    if (!key32) return -3;
+    return crs_any(p, ChaCha20::Key::from_bytes(key32), crs_coeff, crs_fft);
+}
 
+static int party_keygen_any(const mktfhe_params *p, const ChaCha20::Key &seed, int party, const void *crs_coeff, uint32_t *lwekey,
+                            void *ringkey, double *brk, double *rlk, double *pubb, uint32_t *ksk, int nthreads);
 int mktfhe_host_party_keygen(const mktfhe_params *p, uint64_t seed, int party, const void *crs_coeff, uint32_t *lwekey,
                              void *ringkey, double *brk, double *rlk, double *pubb, uint32_t *ksk, int nthreads) {
+    return party_keygen_any(p, ChaCha20::Key::from_seed(seed), party, crs_coeff, lwekey, ringkey, brk, rlk, pubb, ksk, nthreads);
+}
+int mktfhe_host_party_keygen_key(const mktfhe_params *p, const uint8_t *key32, int party, const void *crs_coeff, uint32_t *lwekey,
+                                 void *ringkey, double *brk, double *rlk, double *pubb, uint32_t *ksk, int nthreads) {
+    if (!key32) return -3;
+    return party_keygen_any(p, ChaCha20::Key::from_bytes(key32), party, crs_coeff, lwekey, ringkey, brk, rlk, pubb, ksk, nthreads);
+}
+static int party_keygen_any(const mktfhe_params *p, const ChaCha20::Key &seed, int party, const void *crs_coeff, uint32_t *lwekey,
+                            void *ringkey, double *brk, double *rlk, double *pubb, uint32_t *ksk, int nthreads) {
     if (!lwekey) return -3;
     return mktfhe_torus_bits(p) == 64
                ? party_keygen_impl<uint64_t>(p, seed, party, (const uint64_t *)crs_coeff, lwekey, (uint64_t *)ringkey, brk, rlk, pubb, ksk, nthreads)
                : party_keygen_impl<uint32_t>(p, seed, party, (const uint32_t *)crs_coeff, lwekey, (uint32_t *)ringkey, brk, rlk, pubb, ksk, nthreads);
 }
 
+static int enc_any(const mktfhe_params *p, const ChaCha20::Key &seed, int m, const uint32_t *lwekey, uint32_t *out, uint64_t nonce = 0);
+static int enc_ith_any(const mktfhe_params *p, const ChaCha20::Key &seed, int m, int i, const uint32_t *lwekey_i, uint32_t *out, uint64_t nonce = 0);
+static int enc_full_any(const mktfhe_params *p, const ChaCha20::Key &seed, int m, const uint32_t *lwekeys, uint32_t *out, uint64_t nonce = 0);
 int mktfhe_host_lwe_encrypt(const mktfhe_params *p, uint64_t seed, int m, const uint32_t *lwekey, uint32_t *out) {
-    ChaCha20 rng(seed, stream_id(S_ENC, 0, 0));
+    return enc_any(p, ChaCha20::Key::from_seed(seed), m, lwekey, out);
+}
+int mktfhe_host_lwe_ith_encrypt(const mktfhe_params *p, uint64_t seed, int m, int i, const uint32_t *lwekey_i, uint32_t *out) {
+    return enc_ith_any(p, ChaCha20::Key::from_seed(seed), m, i, lwekey_i, out);
+}
+int mktfhe_host_lwe_encrypt_full(const mktfhe_params *p, uint64_t seed, int m, const uint32_t *lwekeys, uint32_t *out) {
+    return enc_full_any(p, ChaCha20::Key::from_seed(seed), m, lwekeys, out);
+}
+int mktfhe_host_lwe_encrypt_key(const mktfhe_params *p, const uint8_t *key32, int m, const uint32_t *lwekey, uint32_t *out) {
+    return key32 ? enc_any(p, ChaCha20::Key::from_bytes(key32), m, lwekey, out) : -3;
+}
+int mktfhe_host_lwe_ith_encrypt_key(const mktfhe_params *p, const uint8_t *key32, int m, int i, const uint32_t *lwekey_i, uint32_t *out) {
+    return key32 ? enc_ith_any(p, ChaCha20::Key::from_bytes(key32), m, i, lwekey_i, out) : -3;
+}
+int mktfhe_host_lwe_encrypt_full_key(const mktfhe_params *p, const uint8_t *key32, int m, const uint32_t *lwekeys, uint32_t *out) {
+    return key32 ? enc_full_any(p, ChaCha20::Key::from_bytes(key32), m, lwekeys, out) : -3;
+}
+static int enc_any(const mktfhe_params *p, const ChaCha20::Key &seed, int m, const uint32_t *lwekey, uint32_t *out, uint64_t nonce) {
+    ChaCha20 rng(seed, stream_id(S_ENC, 0, 0 | (nonce << 2)));
     uint32_t dot = 0;
     for (int i = 0; i < p->n; i++) { out[1 + i] = rng.u32(); dot += out[1 + i] * lwekey[i]; }
     out[0] = noise<uint32_t>(rng, p->alpha) + ((0u - dot) + mu_of(m));
     return 0;
 }
 
-int mktfhe_host_lwe_ith_encrypt(const mktfhe_params *p, uint64_t seed, int m, int i, const uint32_t *lwekey_i, uint32_t *out) {
+static int enc_ith_any(const mktfhe_params *p, const ChaCha20::Key &seed, int m, int i, const uint32_t *lwekey_i, uint32_t *out, uint64_t nonce) {
     if (i < 0 || i >= p->k) return -1;
-    ChaCha20 rng(seed, stream_id(S_ENC, i, 1));
+    ChaCha20 rng(seed, stream_id(S_ENC, i, 1 | (nonce << 2)));
     memset(out, 0, sizeof(uint32_t) * mktfhe_lwe_words(p));
     uint32_t *a = out + 1 + (size_t)i * p->n, dot = 0;
     for (int j = 0; j < p->n; j++) { a[j] = rng.u32(); dot += a[j] * lwekey_i[j]; }
@@ -365,8 +415,8 @@ int mktfhe_host_lwe_ith_encrypt(const mktfhe_params *p, uint64_t seed, int m, in
     return 0;
 }
 
-int mktfhe_host_lwe_encrypt_full(const mktfhe_params *p, uint64_t seed, int m, const uint32_t *lwekeys, uint32_t *out) {
-    ChaCha20 rng(seed, stream_id(S_ENC, 0, 2));
+static int enc_full_any(const mktfhe_params *p, const ChaCha20::Key &seed, int m, const uint32_t *lwekeys, uint32_t *out, uint64_t nonce) {
+    ChaCha20 rng(seed, stream_id(S_ENC, 0, 2 | (nonce << 2)));
     uint32_t dot = 0;
     const size_t len = (size_t)p->n * p->k;
     for (size_t j = 0; j < len; j++) { out[1 + j] = rng.u32(); dot += out[1 + j] * lwekeys[j]; }
@@ -389,6 +439,60 @@ int mktfhe_host_lwe_decrypt(const mktfhe_params *p, const uint32_t *lwekeys, con
         return ((ph >> 29) + carry) == 1u;
     }
     return ph < 0x80000000u;   // scheme.jl:391-407
+}
+
+// ---- batched forms (scheme.jl:352-407 over many ciphertexts; OpenMP over ciphertexts)
+static int enc_batch_any(const mktfhe_params *p, bool keyed, uint64_t seed0, const uint8_t *key32, int kind, int party, const uint8_t *bits,
+                         size_t count, const uint32_t *lwekeys, uint32_t *out, int nthreads) {
+    if (!bits || !lwekeys || !out || kind < 0 || kind > 2) return -3;
+    const bool mk = p->scheme == MKTFHE_CCS || p->scheme == MKTFHE_KMS || p->scheme == MKTFHE_KMS_BLOCK;
+    if ((kind == 0) == mk) return -1;                       // lwe_encrypt is single-key, the other two multi-key
+    if (kind == 1 && (party < 0 || party >= p->k)) return -1;
+    const size_t lw = mktfhe_lwe_words(p);
+    const ChaCha20::Key k0 = keyed ? ChaCha20::Key::from_bytes(key32) : ChaCha20::Key::from_seed(seed0);
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+#endif
+    for (long long g = 0; g < (long long)count; g++) {
+        // seeded form: ciphertext g is exactly the single call with seed0 + g; keyed form: one key, nonce g
+        const ChaCha20::Key kg = keyed ? k0 : ChaCha20::Key::from_seed(seed0 + (uint64_t)g);
+        const uint64_t nonce = keyed ? (uint64_t)g + 1 : 0;
+        uint32_t *o = out + (size_t)g * lw;
+        if (kind == 0) enc_any(p, kg, bits[g], lwekeys, o, nonce);
+        else if (kind == 1) enc_ith_any(p, kg, bits[g], party, lwekeys, o, nonce);
+        else enc_full_any(p, kg, bits[g], lwekeys, o, nonce);
+    }
+    return 0;
+}
+int mktfhe_host_encrypt_batch(const mktfhe_params *p, uint64_t seed0, int kind, int party, const uint8_t *bits, size_t count,
+                              const uint32_t *lwekeys, uint32_t *out, int nthreads) {
+    return enc_batch_any(p, false, seed0, nullptr, kind, party, bits, count, lwekeys, out, nthreads);
+}
+int mktfhe_host_encrypt_batch_key(const mktfhe_params *p, const uint8_t *key32, int kind, int party, const uint8_t *bits, size_t count,
+                                  const uint32_t *lwekeys, uint32_t *out, int nthreads) {
+    if (!key32) return -3;
+    return enc_batch_any(p, true, 0, key32, kind, party, bits, count, lwekeys, out, nthreads);
+}
+int mktfhe_host_phase_batch(const mktfhe_params *p, const uint32_t *lwekeys, const uint32_t *cts, size_t count, uint32_t *phases_out, int nthreads) {
+    if (!lwekeys || !cts || !phases_out) return -3;
+    const size_t lw = mktfhe_lwe_words(p);
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+#endif
+    for (long long g = 0; g < (long long)count; g++) phases_out[g] = mktfhe_host_lwe_phase(p, lwekeys, cts + (size_t)g * lw);
+    return 0;
+}
+int mktfhe_host_decrypt_batch(const mktfhe_params *p, const uint32_t *lwekeys, const uint32_t *cts, size_t count, uint8_t *bits_out, int nthreads) {
+    if (!lwekeys || !cts || !bits_out) return -3;
+    const size_t lw = mktfhe_lwe_words(p);
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+#endif
+    for (long long g = 0; g < (long long)count; g++) bits_out[g] = (uint8_t)mktfhe_host_lwe_decrypt(p, lwekeys, cts + (size_t)g * lw);
+    return 0;
 }
 
 void mktfhe_host_fft_tables(int N, double *psi, double *psiinv, double *roots, double *rootsinv) {

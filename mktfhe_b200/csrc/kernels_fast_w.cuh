@@ -140,6 +140,20 @@ __device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0,
 __device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// producer-side wait: back off between polls so that the spin does not take issue slots from the compute warps of its scheduler
+__device__ __forceinline__ void mb_wait_sleep(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!fast::mb_try(bar, parity)) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+// ring position of a consumer warp: tile -> (slot, phase parity), advanced without divisions
+struct RingPos {
+    uint32_t slot, par;
+    __device__ __forceinline__ void advance(uint32_t by) { slot += by; if (slot >= RINGW) { slot -= RINGW; par ^= 1; } }
+};
+
 __device__ __forceinline__ cplx unpack_c(const uint32_t (&v)[16], int i) {
     return make_double2(__hiloint2double((int)v[4 * i + 1], (int)v[4 * i]), __hiloint2double((int)v[4 * i + 3], (int)v[4 * i + 2]));
 }
@@ -186,7 +200,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
         if (tid == NCW * 32) {
             for (uint32_t n = 0; n < ntiles; n++) {
                 const int slot = n % RINGW;
-                if (n >= RINGW) mb_wait(&empty[slot], ((n / RINGW) - 1) & 1);
+                if (n >= RINGW) mb_wait_sleep(&empty[slot], ((n / RINGW) - 1) & 1);
                 const uint32_t within = n % (uint32_t)(4 * l), step = n / (uint32_t)(4 * l);
                 const int idx = a.step_mode ? a.step_idx : (int)step;
                 mb_expect_tx(&full[slot], H * 16);
@@ -207,16 +221,25 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
         const size_t unit_out = a.step_mode ? up : (size_t)gate * a.R + (party == 0 ? 0 : 1 + (size_t)(party - 1) * a.l_lev + row);
         const uint32_t tm_acc = tm + (w == 0 ? TMW_ACC_B : TMW_ACC_A), tm_tacc = tm + (w == 0 ? TMW_TACC_B : TMW_TACC_A);
 
-        if (live) {                                                // each warp initialises its half of the RLWE accumulator
-            if (!a.step_mode) {
+        uint64_t cadd = (uint64_t)1 << (64 - l * a.logB - 1);
+        for (int j = 0; j < l; j++) cadd += (uint64_t)1 << (64 - l * a.logB + j * a.logB + a.logB - 1);
+        if (live) {                                                // each warp initialises its half of the RLWE accumulator (+ cadd) and of the sums
+            {
                 uint32_t z[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) z[i] = 0u;
-                const uint64_t gv = (t == 0 && w == 0) ? (uint64_t)1 << (64 - (row + 1) * a.logB_lev) : 0;   // bootstrapping.jl:402-408
+#pragma unroll
+                for (int c = 0; c < 8; c++) tm_st16(tm_tacc + 16 * c, z);
+            }
+            if (!a.step_mode) {
+                uint32_t z[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) { z[i] = (uint32_t)cadd; z[i + 1] = (uint32_t)(cadd >> 32); }
+                const uint64_t gv = cadd + ((t == 0 && w == 0) ? (uint64_t)1 << (64 - (row + 1) * a.logB_lev) : 0);   // bootstrapping.jl:402-408
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    z[0] = c == 0 ? (uint32_t)gv : 0u;
-                    z[1] = c == 0 ? (uint32_t)(gv >> 32) : 0u;
+                    z[0] = c == 0 ? (uint32_t)gv : (uint32_t)cadd;
+                    z[1] = c == 0 ? (uint32_t)(gv >> 32) : (uint32_t)(cadd >> 32);
                     tm_st16(tm_acc + 16 * c, z);
                 }
             } else {
@@ -226,7 +249,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                     uint32_t v[16];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const uint64_t c0 = src[t + 32 * (4 * c + i)], c1 = src[t + 32 * (4 * c + i) + H];
+                        const uint64_t c0 = src[t + 32 * (4 * c + i)] + cadd, c1 = src[t + 32 * (4 * c + i) + H] + cadd;
                         v[4 * i] = (uint32_t)c0; v[4 * i + 1] = (uint32_t)(c0 >> 32); v[4 * i + 2] = (uint32_t)c1; v[4 * i + 3] = (uint32_t)(c1 >> 32);
                     }
                     tm_st16(tm_acc + 16 * c, v);
@@ -239,26 +262,29 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
         }
         const int logB = a.logB;
         const int bit = 64 - l * logB;
-        // divbits rounding + balanced-digit carry chain in one 64-bit add (see kernels_fast.cuh)
-        uint64_t cadd = (uint64_t)1 << (bit - 1);
-        for (int j = 0; j < l; j++) cadd += (uint64_t)1 << (bit + j * logB + logB - 1);
+        // divbits rounding + balanced-digit carry chain in one 64-bit add (see kernels_fast.cuh).  The accumulator is KEPT with
+        // this constant added (acc + cadd mod 2^64): digits are then plain bit fields of the stored words; the constant comes
+        // off again when the accumulator leaves the kernel.
         const uint32_t mask = (1u << logB) - 1;
         const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));
         const uint32_t *at_src = a.step_mode ? a.tilde + up : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
         const int brv5t = (int)(__brev((unsigned)t) >> 27);
+        // this warp's first tile is 2w (digit w, component .b); it consumes tiles 4j + 2w, 4j + 2w + 1 of every step
+        RingPos rp{(uint32_t)(2 * w) % RINGW, 0u};
 
         for (int step = 0; step < nsteps; step++) {
             const uint32_t at = live ? at_src[a.step_mode ? 0 : step] : 0u;
-            const uint32_t tile0 = (uint32_t)step * 4 * l;          // first tile of this step
             if (at == 0) {                                          // :413 / dead unit: keep the ring moving, compute nothing
-                for (int j = 0; j < l; j++)
+                for (int j = 0; j < l; j++) {
 #pragma unroll
                     for (int comp = 0; comp < 2; comp++) {
-                        const uint32_t n = tile0 + (uint32_t)(2 * j + w) * 2 + comp;
-                        mb_wait(&full[n % RINGW], (n / RINGW) & 1);
+                        mb_wait(&full[rp.slot], rp.par);
                         __syncwarp();
-                        if (t == 0) mb_arrive(&empty[n % RINGW]);
+                        if (t == 0) mb_arrive(&empty[rp.slot]);
+                        rp.advance(1);
                     }
+                    rp.advance(2);
+                }
                 continue;
             }
             const cplx m1 = __ldg(&a.tb.emono[((4 * brv5t + 1) * at) & 4095]);
@@ -279,8 +305,8 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                         tm_pin16(v[c]);
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            const uint64_t v0 = (((uint64_t)v[c][4 * i + 1] << 32) | v[c][4 * i]) + cadd;
-                            const uint64_t v1 = (((uint64_t)v[c][4 * i + 3] << 32) | v[c][4 * i + 2]) + cadd;
+                            const uint64_t v0 = ((uint64_t)v[c][4 * i + 1] << 32) | v[c][4 * i];
+                            const uint64_t v1 = ((uint64_t)v[c][4 * i + 3] << 32) | v[c][4 * i + 2];
                             const uint32_t f0 = (uint32_t)(v0 >> sh) & mask, f1 = (uint32_t)(v1 >> sh) & mask;
                             // signed(d_j) - im*signed(d_{j+H}); 2^52 + field is exact in the double's mantissa
                             x[16 * hb + 4 * c + i] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
@@ -288,42 +314,39 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                     }
                 }
                 fft_fwd(x, xb, tw, t);
-                const uint32_t nb = tile0 + (uint32_t)dg * 2, na = nb + 1;
-                mb_wait(&full[nb % RINGW], (nb / RINGW) & 1);
-                mb_wait(&full[na % RINGW], (na / RINGW) & 1);
-                const cplx *kb = ring + (size_t)(nb % RINGW) * H + t, *ka = ring + (size_t)(na % RINGW) * H + t;
                 if (dg != 0) {                                      // token: the previous digit's products are in TMEM
                     nb_sync(w == 0 ? BAR_BA : BAR_AB);
                     tm_fence_after();
                 }
+                // RGSW accumulators += spectrum x key, one output component per pass; the accumulator chunk after the one
+                // being updated is already in flight
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    cplx zb[4], za[4], kcb[4], kca[4];
+                for (int pz = 0; pz < 2; pz++) {
+                    mb_wait(&full[rp.slot], rp.par);
+                    const cplx *kp = ring + (size_t)rp.slot * H + t;
+                    const uint32_t tmz = tm + (pz == 0 ? TMW_TACC_B : TMW_TACC_A);
+                    uint32_t v[2][16];
+                    tm_ld16(tmz, v[0]);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) { kcb[i] = kb[(4 * c + i) * 32]; kca[i] = ka[(4 * c + i) * 32]; }
-                    if (dg == 0) {
+                    for (int c = 0; c < 8; c++) {
+                        cplx kc[4], z[4];
 #pragma unroll
-                        for (int i = 0; i < 4; i++) { zb[i] = cmul_f(x[4 * c + i], kcb[i]); za[i] = cmul_f(x[4 * c + i], kca[i]); }
-                    } else {
-                        uint32_t vb[16], va[16];
-                        tm_ld16(tm + TMW_TACC_B + 16 * c, vb);
-                        tm_ld16(tm + TMW_TACC_A + 16 * c, va);
+                        for (int i = 0; i < 4; i++) kc[i] = kp[(4 * c + i) * 32];
                         tm_wait_ld();
-                        tm_pin16(vb); tm_pin16(va);
+                        tm_pin16(v[c & 1]);
+                        if (c < 7) tm_ld16(tmz + 16 * (c + 1), v[(c + 1) & 1]);
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            zb[i] = cmac_f(unpack_c(vb, i), x[4 * c + i], kcb[i]);
-                            za[i] = cmac_f(unpack_c(va, i), x[4 * c + i], kca[i]);
-                        }
+                        for (int i = 0; i < 4; i++) z[i] = cmac_f(unpack_c(v[c & 1], i), x[4 * c + i], kc[i]);
+                        tm_st_c4(tmz + 16 * c, z);
                     }
-                    tm_st_c4(tm + TMW_TACC_B + 16 * c, zb);
-                    tm_st_c4(tm + TMW_TACC_A + 16 * c, za);
+                    __syncwarp();
+                    if (t == 0) mb_arrive(&empty[rp.slot]);         // this key tile is done
+                    rp.advance(1);
                 }
+                rp.advance(2);                                      // skip the other warp's digit
                 tm_wait_st();
                 tm_fence_before();
                 nb_arrive(w == 0 ? BAR_AB : BAR_BA);                // pass the token
-                __syncwarp();
-                if (t == 0) { mb_arrive(&empty[nb % RINGW]); mb_arrive(&empty[na % RINGW]); }
             }
             if (w == 0) {                                           // B's last product closes the sums
                 nb_sync(BAR_BA);
@@ -344,6 +367,13 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
 #pragma unroll
                         for (int i = 0; i < 4; i++) y[16 * hb + 4 * c + i] = unpack_c(v[c], i);
                     }
+                }
+                {   // clear the sums for the next step (every product accumulates, also the first)
+                    uint32_t z[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) z[i] = 0u;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) tm_st16(tm_tacc + 16 * c, z);
                 }
                 // slot 32t + e evaluates at exp(-i*pi*(4*brv10(n)+1)/N), brv10(n) = 32*brv5(e) + brv5(t)
 #pragma unroll
@@ -374,7 +404,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                 tm_wait_st();
             }
             tm_fence_before();
-            nb_sync(BAR_STEP);                                      // both halves of the accumulator are updated
+            nb_sync(BAR_STEP);                                      // both halves of the accumulator are updated, the sums are clear
             tm_fence_after();
         }
 
@@ -393,7 +423,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                         tm_pin16(v[c]);
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            const uint64_t v0 = ((uint64_t)v[c][4 * i + 1] << 32) | v[c][4 * i], v1 = ((uint64_t)v[c][4 * i + 3] << 32) | v[c][4 * i + 2];
+                            const uint64_t v0 = (((uint64_t)v[c][4 * i + 1] << 32) | v[c][4 * i]) - cadd, v1 = (((uint64_t)v[c][4 * i + 3] << 32) | v[c][4 * i + 2]) - cadd;
                             x[16 * hb + 4 * c + i] = make_double2(__ll2double_rn((long long)v0), __ll2double_rn((long long)((uint64_t)0 - v1)));
                         }
                     }
@@ -416,8 +446,8 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                     tm_pin16(v);
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        dst[t + 32 * (4 * c + i)] = ((uint64_t)v[4 * i + 1] << 32) | v[4 * i];
-                        dst[t + 32 * (4 * c + i) + H] = ((uint64_t)v[4 * i + 3] << 32) | v[4 * i + 2];
+                        dst[t + 32 * (4 * c + i)] = (((uint64_t)v[4 * i + 1] << 32) | v[4 * i]) - cadd;
+                        dst[t + 32 * (4 * c + i) + H] = (((uint64_t)v[4 * i + 3] << 32) | v[4 * i + 2]) - cadd;
                     }
                 }
             }

@@ -12,8 +12,10 @@ should read like test/KMS.jl or test/CGGI.jl:
     lwekey, ringkey, scheme = setup(params)                  # single-key schemes, scheme.jl:151,190
 
 Differences that cannot be avoided: Julia's `!` is spelled `_` (`bootstrapping_`, `NOT_`), ciphertexts are uint32 arrays
-`[b, a...]` instead of `LWE` structs, and randomness is a seeded ChaCha20 stream (pass `seed=` for reproducible keys and
-ciphertexts; by default every call draws a fresh seed from the OS, like the reference's unseeded streams).
+`[b, a...]` instead of `LWE` structs.  Randomness: by default every call (CRS, each party's keygen, each encryption) draws
+its own 256-bit ChaCha20 key from the OS CSPRNG, like the reference's unseeded `ChaCha20Stream()` calls -- a party's secrets
+are unrelated to the public CRS and to every other party.  `seed=<int>` makes a call reproducible for tests; such keys and
+ciphertexts are not secret (64-bit seed) and a seed must never be reused for two encryptions.
 """
 from __future__ import annotations
 
@@ -29,15 +31,15 @@ from .params import Params
 from .scheme import Scheme
 
 
-def _fresh_seed() -> int:
-    return int.from_bytes(os.urandom(7), "little")
+def _fresh_seed() -> bytes:
+    return _host.fresh_key()
 
 
 @dataclass
 class CommonReferenceString:
-    """`a = CRS(params)`: l_uni uniform polynomials (coefficient form for keygen, FFT form for the evaluator)."""
+    """`a = CRS(params)`: l_uni uniform polynomials (coefficient form for keygen, FFT form for the evaluator).  Public data:
+    it carries no seed, and nothing secret is ever derived from it."""
     params: Params
-    seed: int
     coeff: np.ndarray
     fft: np.ndarray
     _next_party: int = 0
@@ -61,20 +63,20 @@ class BootKey:
 def CRS(params: Params, seed: int | None = None) -> CommonReferenceString:
     if not params.is_mk:
         raise TypeError("CRS is defined for the multi-key parameter sets (CCS*, KMS*) only")
-    seed = _fresh_seed() if seed is None else int(seed)
-    coeff, fft = _host.crs(params, seed)
-    return CommonReferenceString(params, seed, coeff, fft)
+    coeff, fft = _host.crs(params, _fresh_seed() if seed is None else int(seed))
+    return CommonReferenceString(params, coeff, fft)
 
 
-def party_keygen(a: CommonReferenceString, params: Params, nthreads: int = 0):
-    """-> (lwekey, ringkey, btk) for the next party, so that `first.(keys)` / `last.(keys)` of test/KMS.jl:10-12 carry over."""
+def party_keygen(a: CommonReferenceString, params: Params, nthreads: int = 0, seed: int | None = None):
+    """-> (lwekey, ringkey, btk) for the next party, so that `first.(keys)` / `last.(keys)` of test/KMS.jl:10-12 carry over.
+    The party's secrets come from its own fresh 256-bit key (seed=<int>: reproducible, for tests only)."""
     if a.params != params:
         raise ValueError("the CRS was made for a different parameter set")
     if a._next_party >= params.k:
         raise ValueError(f"all {params.k} parties of this CRS already have keys")
     party = a._next_party
     a._next_party += 1
-    q = _host.party_keygen(params, a.seed, party, a.coeff, nthreads)
+    q = _host.party_keygen(params, _fresh_seed() if seed is None else int(seed), party, a.coeff, nthreads)
     return LWEkey(q["lwekey"]), q["ringkey"], BootKey(party, q["brk"], q["ksk"], q["rlk"], q["pubb"])
 
 
@@ -112,11 +114,8 @@ def lwe_encrypt(m, key: LWEkey, params: Params, seed: int | None = None) -> np.n
     """Single-key `lwe_encrypt(m, key, params)`: scheme.jl:352-368."""
     if params.is_mk:
         raise TypeError("use lwe_ith_encrypt for multi-key parameter sets")
-    out = np.empty(params.lwe_words, dtype=np.uint32)
-    cp = params.c_struct()
-    _host.lib().mktfhe_host_lwe_encrypt(ctypes.byref(cp), _fresh_seed() if seed is None else int(seed), int(bool(m)),
-                                        _host.ptr(np.ascontiguousarray(key.key)), _host.ptr(out))
-    return out
+    return _host.encrypt_batch(params, _fresh_seed() if seed is None else int(seed), _host.ENC_SINGLE, 0, [bool(m)],
+                               np.ascontiguousarray(key.key), 1)[0]
 
 
 def lwe_ith_encrypt(m, i: int, key: LWEkey, params: Params, seed: int | None = None) -> np.ndarray:
@@ -125,13 +124,8 @@ def lwe_ith_encrypt(m, i: int, key: LWEkey, params: Params, seed: int | None = N
         raise TypeError("use lwe_encrypt for single-key parameter sets")
     if not 1 <= int(i) <= params.k:
         raise IndexError(f"party index {i} outside 1..{params.k}")
-    out = np.empty(params.lwe_words, dtype=np.uint32)
-    cp = params.c_struct()
-    rc = _host.lib().mktfhe_host_lwe_ith_encrypt(ctypes.byref(cp), _fresh_seed() if seed is None else int(seed), int(bool(m)),
-                                                 int(i) - 1, _host.ptr(np.ascontiguousarray(key.key)), _host.ptr(out))
-    if rc != 0:
-        raise IndexError(f"party index {i} rejected by the host library")
-    return out
+    return _host.encrypt_batch(params, _fresh_seed() if seed is None else int(seed), _host.ENC_ITH, int(i) - 1, [bool(m)],
+                               np.ascontiguousarray(key.key), 1)[0]
 
 
 def lwe_decrypt(lwe, key, params: Params | None = None) -> bool:

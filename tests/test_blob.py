@@ -40,6 +40,15 @@ def test_evaluation_only_blob_has_no_secrets(tmp_path):
         lk.lwe_decrypt(np.zeros(ks.params.lwe_words, dtype=np.uint32))
     raw = open(path, "rb").read()
     assert ks.parties[0]["lwekey"].tobytes() not in raw
+    # the seed regenerates every secret, so an evaluation-only blob must not carry it
+    import json, struct
+    hlen = struct.unpack("<II", raw[8:16])[1]
+    header = json.loads(raw[16:16 + hlen].decode())
+    assert header["seed"] is None and lk.seed is None
+    assert str(ks.seed).encode() not in raw[:16 + hlen]
+    path2 = str(tmp_path / "full.blob")
+    blob.save_keys(path2, ks, include_secret=True)
+    assert blob.load_keys(path2).seed == ks.seed
 
 
 def test_ciphertext_blob_and_header_validation(tmp_path):

@@ -119,11 +119,13 @@ def test_fast_vs_strict_decrypt_and_noise(gpu_schemes, name):
             want = np.array([PLAIN[op](bool(x), bool(y)) for x, y in zip(b1, b2)])
             ok += int(np.sum(ks.decrypt_batch(out) == want))
             errs.append(_phase_errors(ks, out, want))
-        stats[mode] = (ok, float(np.concatenate(errs).std()))
+        # median |error| * 1.4826 = sigma for a Gaussian, and unlike the sample std it is not dominated by the few wrapped
+        # phases (|error| ~ 2^31) of the sets that sit at the decision margin
+        stats[mode] = (ok, 1.4826 * float(np.median(np.abs(np.concatenate(errs)))))
     s.set_mode(MODE_FAST)
     (ok_s, sd_s), (ok_f, sd_f) = stats[MODE_STRICT], stats[MODE_FAST]
-    print(f"{name}: STRICT ok {ok_s}/{2 * B} std 2^{np.log2(sd_s):.2f}; FAST ok {ok_f}/{2 * B} std 2^{np.log2(sd_f):.2f} (margin 2^29)")
-    assert 0.8 < sd_f / sd_s < 1.25
+    print(f"{name}: STRICT ok {ok_s}/{2 * B} sigma 2^{np.log2(sd_s):.2f}; FAST ok {ok_f}/{2 * B} sigma 2^{np.log2(sd_f):.2f} (margin 2^29)")
+    assert 0.75 < sd_f / sd_s < 1.33
     if name in ("CCS16party", "KMS32party", "KMS32partyblock"):
         # at the margin by construction of the parameter set: both modes must show the same failure level
         assert abs(ok_f - ok_s) <= 8 and min(ok_f, ok_s) >= 0.85 * 2 * B
@@ -155,10 +157,10 @@ def test_failure_rate_matches_oracle(gpu_schemes, name):
     out_f = s.gate(0, c1, c2)
     fail_f = int(np.sum(ks.decrypt_batch(out_f) != want))
     fail_o = int(np.sum(gold["dec"] != gold["want"]))
-    sd_f = _phase_errors(ks, out_f, want).std()
-    sd_o = gold["phase_err"].astype(np.float64).std()
+    sd_f = 1.4826 * np.median(np.abs(_phase_errors(ks, out_f, want)))           # robust sigma, see above
+    sd_o = 1.4826 * np.median(np.abs(gold["phase_err"].astype(np.float64)))
     print(f"{name}: {count} MK-NAND gates: oracle failures {fail_o} ({100 * fail_o / count:.2f} %), FAST failures {fail_f} "
-          f"({100 * fail_f / count:.2f} %); phase-error std oracle 2^{np.log2(sd_o):.2f}, FAST 2^{np.log2(sd_f):.2f}")
+          f"({100 * fail_f / count:.2f} %); phase-error sigma oracle 2^{np.log2(sd_o):.2f}, FAST 2^{np.log2(sd_f):.2f}")
     # two independent binomial draws of the same rate differ by less than 4 sigma of their difference
     pbar = max((fail_f + fail_o) / (2.0 * count), 1.0 / count)
     assert abs(fail_f - fail_o) <= 4.0 * np.sqrt(2.0 * count * pbar * (1 - pbar)) + 1

@@ -41,7 +41,7 @@ def test_keys_match_the_keyset_generator():
     params = P.KMS2party
     ks = keyset("KMS2party")
     a = CRS(params, seed=ks.seed)
-    lwekey, ringkey, btk = party_keygen(a, params)
+    lwekey, ringkey, btk = party_keygen(a, params, seed=ks.seed)
     assert np.array_equal(lwekey.key, ks.parties[0]["lwekey"]) and np.array_equal(btk.ksk, ks.parties[0]["ksk"])
     assert np.array_equal(btk.brk, ks.parties[0]["brk"]) and np.array_equal(a.fft, ks.crs_fft)
 
@@ -53,6 +53,32 @@ def test_fresh_randomness_by_default():
     assert not np.array_equal(c1, c2) and lwe_decrypt(c1, key, params) and lwe_decrypt(c2, key, params)
     assert np.array_equal(lwe_encrypt(0, key, params, seed=9), lwe_encrypt(0, key, params, seed=9))
     assert lwe_decrypt(lwe_encrypt(0, key, params), key, params) is False
+
+
+def test_party_secrets_are_independent_of_the_crs_and_of_each_other():
+    """a party's secret keys must not be derivable from the public CRS.  By default every party_keygen call
+    draws its own 256-bit key from the OS: two key generations over the SAME CRS give unrelated secrets, the CRS object carries
+    no seed, and two parties never share a secret."""
+    params = P.CCS2party
+    a1, a2 = CRS(params, seed=7), CRS(params, seed=7)
+    assert np.array_equal(a1.coeff, a2.coeff) and not hasattr(a1, "seed")
+    k1 = [party_keygen(a1, params)[0].key for _ in range(params.k)]
+    k2 = [party_keygen(a2, params)[0].key for _ in range(params.k)]
+    assert not np.array_equal(k1[0], k2[0]) and not np.array_equal(k1[1], k2[1])      # same public CRS, fresh secrets
+    assert not np.array_equal(k1[0], k1[1])
+    assert not np.array_equal(CRS(params).coeff, CRS(params).coeff)
+
+
+def test_keyset_default_seed_is_random():
+    from mktfhe_b200.keys import KeySet
+    p = P.CGGIparam
+    k1, k2 = KeySet(p, want_ksk=False, secret_only=True), KeySet(p, want_ksk=False, secret_only=True)
+    assert k1.seed is None and not np.array_equal(k1.lwekeys, k2.lwekeys)
+    c1, c2 = k1.lwe_encrypt(1), k1.lwe_encrypt(1)                # fresh randomness per encryption
+    assert not np.array_equal(c1, c2) and k1.lwe_decrypt(c1) and k1.lwe_decrypt(c2)
+    assert np.array_equal(k1.lwe_encrypt(1, 5), k1.lwe_encrypt(1, 5))
+    batch = k1.encrypt_batch([1, 0, 1])
+    assert not np.array_equal(batch[0, 1:], batch[2, 1:]) and list(k1.decrypt_batch(batch)) == [True, False, True]
 
 
 def test_argument_errors():
