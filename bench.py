@@ -31,10 +31,6 @@ UNIT = "gates/s"
 KEY_SEED = 0x4D4B5446
 GATE_SEED = 0x47415445
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default batch, from `ncu` captures committed under
-# profiles/ (r1_traffic_kms2.csv); null for workloads not captured.
-TRAFFIC = {"kms2": {"phase1": 2451908096 + 398664704, "keyswitch": 437774592 + 56238336, "phase2": 459913728 + 615687168}}
-
 WORKLOADS = {  # name -> (parameter set, default per-GPU batch)
     "kms2": ("KMS2party", 4096),
     "kms8block": ("KMS8partyblock", 2048),
@@ -187,6 +183,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="gates per GPU per step (default: the workload's)")
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the sub-lines for the other BASELINE configurations")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -244,15 +241,76 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from mktfhe_b200.scheme import MODE_FAST, MODE_STRICT, setup
+    ctx = {"rank": rank, "world": world, "local_rank": local_rank, "torch": torch, "dist": dist, "mode": args.mode}
+    line, rc = run_workload(ctx, args.workload, batch, args.steps, args.warmup, headline=True,
+                            want_cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+    # the other configurations BASELINE.json names, each as a full sub-line (fewer steps: they are reported, the headline is timed
+    # to the contract).  Under torchrun every rank runs them too, so the scaling record carries KMS32 and KMS8block at N GPUs.
+    if args.workload == "kms2" and not args.no_also and not args.batch:
+        also = []
+        for wl in ALSO:
+            sub, rc2 = run_workload(ctx, wl, WORKLOADS[wl][1], ALSO_STEPS, ALSO_WARMUP, headline=False, want_cpu_baseline=False)
+            rc = rc or rc2
+            if rank == 0:
+                also.append(sub)
+        if rank == 0:
+            line["also"] = also
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return rc
+
+
+# BASELINE.json configs[0] (CGGI), configs[2] (KMS 8-party block, 16384 gates over 8 GPUs = 2048 per GPU), configs[4] (KMS 32-party)
+ALSO = ("cggi", "kms8block", "kms32")
+ALSO_STEPS, ALSO_WARMUP = 2, 1
+# Fraction of the sampled outputs that must decrypt correctly for the line to count (exit code 3 and "valid": false otherwise).
+# CCS16party / KMS32party sit at the decision margin in the reference algorithm itself: the CPU oracle fails 1.6 % of KMS32party
+# gates and ~5 % of CCS16party gates on the same inputs (tests/golden/failrate_*.npz).
+MIN_OK = {"kms32": 0.93, "kms32block": 0.93, "ccs16": 0.85}
+SMEM_BYTES_PER_CLK_PER_SM = 128
+
+
+def traffic_record():
+    """dram bytes per launch from the committed ncu capture, valid only for the kernel sources it was taken with."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        rec = json.load(open(path))
+    except Exception:
+        return {}, "no capture (profiles/traffic.json)"
+    h = hashlib.sha256()
+    for f in rec.get("sources", []):
+        try:
+            h.update(open(os.path.join(ROOT, f), "rb").read())
+        except OSError:
+            return {}, "capture lists a missing source file"
+    if h.hexdigest() != rec.get("sources_sha256"):
+        return {}, "capture is stale: kernel sources changed since profiles/traffic.json was taken"
+    return rec.get("workloads", {}), f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch ({rec.get('capture', 'profiles/')})"
+
+
+def run_workload(ctx, workload, batch, steps, warmup, headline, want_cpu_baseline):
+    torch, dist = ctx["torch"], ctx["dist"]
+    rank, world, local_rank = ctx["rank"], ctx["world"], ctx["local_rank"]
+    from mktfhe_b200 import params as P
+    from mktfhe_b200.scheme import MODE_FAST, MODE_STRICT
     from mktfhe_b200 import dist as mkdist
+    pname, _ = WORKLOADS[workload]
+    p = P.ALL[pname]
+    cfg = {"workload": f"{pname} MK-NAND, {batch} gates per GPU per step, full-support inputs",
+           "params": pname, "batch_per_gpu": batch, "parties": p.k,
+           "l2_policy": "working set > L2: keys + per-step accumulators exceed 126 MB, no flush needed",
+           "key_seed": KEY_SEED, "gate_seed": GATE_SEED}
 
     t_k = time.perf_counter()
-    scheme, ks = mkdist.setup_replicated(p, KEY_SEED, local_rank, rank, world)
+    scheme, ks, key_times = mkdist.setup_replicated(p, KEY_SEED, local_rank, rank, world, timings=True)
     keygen_s = time.perf_counter() - t_k
-    want = MODE_FAST if args.mode == "fast" else MODE_STRICT
+    want_mode = MODE_FAST if ctx["mode"] == "fast" else MODE_STRICT
     try:
-        scheme.set_mode(want)
+        scheme.set_mode(want_mode)
     except Exception:
         pass
     mode_name = "fast" if scheme.mode == MODE_FAST else "strict"
@@ -282,13 +340,13 @@ def main():
         torch.cuda.synchronize()
         scheme.sync()
 
-    def timed(fn, steps):
+    def timed(fn, nsteps):
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         barrier()
         with torch.cuda.stream(stream):
             ev0.record(stream)
-            for _ in range(steps):
+            for _ in range(nsteps):
                 fn()
             ev1.record(stream)
         barrier()
@@ -299,13 +357,13 @@ def main():
             ms = float(t.item())
         return ms
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_dev()
     scheme.sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
-    ms_dev = timed(step_dev, args.steps)
+    ms_dev = timed(step_dev, steps)
     stage_ms, launches = scheme.last_stage_ms()
     clocks = sampler.stop()
 
@@ -314,41 +372,51 @@ def main():
     ncheck = min(batch, 256)
     want = ~(m1[:ncheck] & m2[:ncheck])
     ok = int(np.sum(ks.decrypt_batch(res[:ncheck]) == want))
-    perr = []
-    for g in range(ncheck):                    # output phase error on Torus32 (decision margin 2^29)
-        e = (ks.phase(res[g]) - ((1 << 29) if want[g] else (7 << 29))) & 0xFFFFFFFF
-        perr.append(e - (1 << 32) if e >= (1 << 31) else e)
+    ph = ks.phase_batch(res[:ncheck]).astype(np.int64)
+    perr = (ph - np.where(want, 1 << 29, 7 << 29)) & 0xFFFFFFFF      # output phase error on Torus32 (decision margin 2^29)
+    perr = np.where(perr >= (1 << 31), perr - (1 << 32), perr).astype(np.float64)
     perr_std_log2 = float(np.log2(np.std(perr) + 1.0))
 
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(min(warmup, 1)):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, steps)
     ok_e2e = int(np.sum(ks.decrypt_batch(hout.numpy().view(np.uint32)[:ncheck]) == want))
 
-    total_gates = batch * world * args.steps
+    total_gates = batch * world * steps
     value = total_gates / (ms_dev * 1e-3)
     e2e_value = total_gates / (ms_e2e * 1e-3)
+    need = MIN_OK.get(workload, 1.0) * ncheck
+    valid = ok >= need and ok_e2e >= need
+    if world > 1:                                  # a wrong result on any rank invalidates the line
+        t = torch.tensor([1.0 if valid else 0.0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        valid = bool(t.item() > 0.5)
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "ms_per_gate": ms_dev / args.steps / batch, "higher_is_better": True,
+    line = {"metric": METRIC, "value": value if valid else None, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_dev / steps, "ms_per_gate": ms_dev / steps / batch, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "mode": mode_name, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * batch * lw * 4, "d2h_bytes_per_step": batch * lw * 4,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches * args.steps,
-            "decrypt_check": {"checked": ncheck, "ok_device_leg": ok, "ok_e2e_leg": ok_e2e, "phase_error_std_log2": perr_std_log2,
+            "mode": mode_name, "clocks": clocks, "valid": valid,
+            "e2e": {"value": e2e_value if valid else None, "unit": UNIT, "h2d_bytes_per_step": 2 * batch * lw * 4, "d2h_bytes_per_step": batch * lw * 4,
+                    "ms_per_step": ms_e2e / steps},
+            "gpu_launches": launches * steps,
+            "decrypt_check": {"checked": ncheck, "ok_device_leg": ok, "ok_e2e_leg": ok_e2e, "required": int(np.ceil(need)),
+                              "phase_error_std_log2": perr_std_log2,
                               "note": "decision margin 2^29; CCS16 / KMS32 sets sit close to it in the reference algorithm itself (DESIGN.md)"},
-            "stage_ms_last_step": stage_ms, "keygen_and_upload_s": keygen_s}
+            "stage_ms_last_step": stage_ms, "keygen_and_upload_s": keygen_s, "key_setup": key_times}
+    if not valid:
+        line["invalid"] = f"decrypt check failed: {ok}/{ncheck} (device leg), {ok_e2e}/{ncheck} (end to end), {int(np.ceil(need))} required"
 
     if rank == 0:
         # roofline of the dominant kernel (phase 1: FP64 FFT + pointwise MAC), measured live
         alg = algorithmic_gflop_per_gate(p)
-        dom = "phase1"
-        dom_ms = stage_ms[dom]
+        traffic, traffic_note = traffic_record()
+        dom_ms = stage_ms["phase1"]
         peak = scheme.dfma_peak_tflops()
         ach = alg["phase1"] * batch / (dom_ms * 1e-3) / 1e3 if dom_ms > 0 else 0.0
-        line["roofline"] = {"bound": "fp64", "kernel": "blind rotation (FP64 transforms + pointwise MAC): fast::k_phase1_tma / k_rgsw_tm / k_ccs_fast", "achieved": ach, "peak": peak,
-                            "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": TRAFFIC.get(args.workload, {}).get("phase1"),
+        line["roofline"] = {"bound": "fp64", "kernel": "blind rotation (FP64 transforms + pointwise MAC): fastw::k_phase1_w / fast::k_phase1_tma<3> / fast32::k_rgsw_tm / k_ccs_fast",
+                            "achieved": ach, "peak": peak,
+                            "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": traffic.get(workload, {}).get("phase1"),
+                            "traffic_source": traffic_note,
                             "peak_source": "measured in this run: register-only DFMA loop, 16 chains x 16 warps/SM (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
                             "algorithmic_gflop_per_gate": alg, "kernel_ms_per_launch": dom_ms}
         try:
@@ -356,21 +424,28 @@ def main():
             src = "measured (MEASURED_PEAKS.json)"
         except Exception:
             hbm, src = 6650.0, "fallback (B200_PROFILING.md)"
+        # Key switch: every gate adds k * 3/4 * N_ks * f rows of (n + 1) words.  The tiled kernel brings a candidate row into shared
+        # memory once per 32 gates (TMA) and each gate reads the row its digit selects from there, so the algorithmic bytes move
+        # through SHARED memory (128 B/clk/SM), not DRAM: that is the pipe the kernel is bound by (ncu: shared pipe 60 %).
         ks_ms = stage_ms["keyswitch"]
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        smem_peak = SMEM_BYTES_PER_CLK_PER_SM * sm_count * sm_mhz * 1e6 / 1e9
         ks_ach = alg["ks_bytes"] * batch / (ks_ms * 1e-3) / 1e9 if ks_ms > 0 else 0.0
-        line["roofline_keyswitch"] = {"bound": "hbm", "achieved": ks_ach, "peak": hbm, "unit": "GB/s", "frac": ks_ach / hbm,
-                                      "peak_source": src, "traffic": TRAFFIC.get(args.workload, {}).get("keyswitch"),
-                                      "kernel_ms_per_launch": ks_ms,
-                                      "note": "algorithmic bytes = ksk rows gathered per gate (SURVEY 8(d)); the tiled kernel fetches each row once "
-                                              "per 32 gates, so achieved exceeds the DRAM peak and traffic is far below the algorithmic bytes"}
-        if world == 1 and not args.no_cpu_baseline:
+        ks_dram = traffic.get(workload, {}).get("keyswitch")
+        line["roofline_keyswitch"] = {"bound": "shared-memory", "achieved": ks_ach, "peak": smem_peak, "unit": "GB/s", "frac": ks_ach / smem_peak,
+                                      "peak_source": f"128 B/clk/SM x {sm_count} SMs x {sm_mhz:.0f} MHz (SM clock sampled during the run)",
+                                      "traffic": ks_dram, "traffic_source": traffic_note,
+                                      "hbm": {"achieved": (ks_dram / (ks_ms * 1e-3) / 1e9) if (ks_dram and ks_ms > 0) else None, "peak": hbm, "peak_source": src,
+                                              "note": "DRAM side: measured bytes / kernel time; rows are fetched once per 32-gate tile"},
+                                      "kernel_ms_per_launch": ks_ms}
+        if want_cpu_baseline:
             info, _, _ = cpu_baseline(ks, c1, c2)
             line["cpu_baseline"] = info
-        emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    scheme.close()
+    del d1, d2, dout, h1, h2, hout
+    torch.cuda.empty_cache()
+    return line, (0 if valid else 3)
 
 
 if __name__ == "__main__":

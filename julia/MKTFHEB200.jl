@@ -70,14 +70,17 @@ function flatten_unienc(u)          # TransUniEnc: d[j], f.stack[j].b, f.stack[j
     buf
 end
 flatten_polys(v) = (buf = Float64[]; foreach(p -> poly!(buf, p), v); buf)
-function flatten_ksk(ksk, n)        # Array{LEV,2}(Dk, N): [c][digit][level][b, a...]; undef entries (block) -> zeros
+function flatten_ksk(ksk, n, f)     # Array{LEV}(Dk, N) or (Dk, N, 1): [c][digit][level][b, a...]; undef entries (block) -> zeros
     Dk, N = size(ksk, 1), size(ksk, 2)
-    f = 8
+    # no slicing: `ksk[:, :, 1]` would touch the #undef entries of a block key (keygen.jl:43-52) and throw UndefRefError
+    entry(dg, c) = ndims(ksk) == 3 ? (isassigned(ksk, dg, c, 1) ? ksk[dg, c, 1] : nothing) :
+                                     (isassigned(ksk, dg, c) ? ksk[dg, c] : nothing)
     buf = zeros(UInt32, N * Dk * f * (n + 1))
     pos = 1
     for c = 1 : N, dg = 1 : Dk
-        if isassigned(ksk, dg, c)
-            for lwe in ksk[dg, c].stack
+        lev = entry(dg, c)
+        if lev !== nothing
+            for lwe in lev.stack
                 buf[pos] = lwe.b; buf[pos+1 : pos+n] = lwe.a; pos += n + 1
             end
         else
@@ -98,7 +101,7 @@ function upload(scheme, params; device::Integer = 0)
         brk = cp[].scheme == CCS_ ? reduce(vcat, flatten_unienc.(btk.brk)) : flatten_rgsw(btk.brk)
         rlk = hasproperty(btk, :rlk) ? flatten_unienc(btk.rlk) : Float64[]
         pub = hasproperty(btk, :b) ? flatten_polys(btk.b) : Float64[]
-        ksk = flatten_ksk(ndims(btk.ksk) == 3 ? btk.ksk[:, :, 1] : btk.ksk, n)
+        ksk = flatten_ksk(btk.ksk, n, Int(cp[].f))
         GC.@preserve brk rlk pub ksk check(ccall((:mktfhe_upload_party_key, LIB), Cint,
             (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt32}),
             h[], i - 1, brk, isempty(rlk) ? C_NULL : pointer(rlk), isempty(pub) ? C_NULL : pointer(pub), ksk), h[])

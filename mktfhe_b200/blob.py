@@ -138,3 +138,30 @@ def load_ciphertexts(path: str, params: Params | None = None, mmap: bool = False
     if params is not None and dataclasses.asdict(p) != dataclasses.asdict(params):
         raise BlobError(f"{path}: ciphertexts of parameter set {p.name}, expected {params.name}")
     return arrays["lwe"]
+
+
+# ---- reference fixtures (julia/dump_fixtures.jl) -----------------------------------------------------------
+
+FIXTURE_GATES = ("NAND", "AND", "OR", "XOR", "XNOR", "NOR")
+
+
+def save_fixture(path: str, params: Params, arrays: dict) -> int:
+    """Write a "fixture" blob: input pairs, the outputs of all six gates and the intermediate stages of NAND
+    (the arrays julia/dump_fixtures.jl writes from a run of the reference)."""
+    return _write(path, "fixture", params, None, list(arrays.items()))
+
+
+def load_fixture(path: str, verify: bool = True):
+    """-> (params, {name: array}) of a fixture blob; checks that every expected array is present and consistent."""
+    _h, p, a = _read(path, "fixture", mmap=False, verify=verify)
+    need = ["in1", "in2", "bits1", "bits2", "nand_linear", "nand_tilde", "nand_acc"] + [f"out_{g}" for g in FIXTURE_GATES]
+    missing = [n for n in need if n not in a]
+    if missing:
+        raise BlobError(f"{path}: fixture lacks {missing}")
+    B = a["in1"].shape[0]
+    for n in need:
+        if a[n].shape[0] != B:
+            raise BlobError(f"{path}: array {n} has {a[n].shape[0]} rows, expected {B}")
+    if a["in1"].shape[1] != p.lwe_words or a["nand_acc"].shape[1:] != (p.k + 1, p.N):
+        raise BlobError(f"{path}: array shapes do not match parameter set {p.name}")
+    return p, a

@@ -60,12 +60,16 @@ def broadcast_keys(ks: KeySet | None, p: Params, device, src: int = 0):
     return parties, crs
 
 
-def setup_replicated(p: Params, seed: int, device_index: int, rank: int, world: int):
+def setup_replicated(p: Params, seed: int, device_index: int, rank: int, world: int, timings: bool = False):
     """Key generation on rank 0, NCCL broadcast, upload from device memory on every rank.
-    Returns (Scheme, KeySet); ranks other than 0 hold secret keys only (for encrypting / checking their shard)."""
+    Returns (Scheme, KeySet); ranks other than 0 hold secret keys only (for encrypting / checking their shard).
+    timings=True appends {"keygen_s", "broadcast_s", "upload_finalize_s", "key_bytes"} (this rank's wall clock)."""
     from .scheme import Scheme
     import os
+    import time
+    t0 = time.perf_counter()
     ks = KeySet(p, seed=seed, secret_only=(rank != 0), nthreads=max(1, len(os.sched_getaffinity(0)) // max(1, min(world, 8))) if rank else len(os.sched_getaffinity(0)))
+    t1 = t2 = time.perf_counter()
     s = Scheme(p, device_index)
     if world == 1:
         for i, q in enumerate(ks.parties):
@@ -74,8 +78,11 @@ def setup_replicated(p: Params, seed: int, device_index: int, rank: int, world: 
             s.upload_common(ks.crs_fft)
     else:
         dev = torch.device("cuda", device_index)
+        dist.barrier()                                   # the other ranks wait here for rank 0's key generation
+        t1 = time.perf_counter()
         parties, crs = broadcast_keys(ks if rank == 0 else None, p, dev)
         torch.cuda.synchronize()
+        t2 = time.perf_counter()
         for i, d in enumerate(parties):
             s.upload_party_ptr(i, d["brk"].data_ptr(), d["ksk"].data_ptr(),
                                d["rlk"].data_ptr() if "rlk" in d else None, d["pubb"].data_ptr() if "pubb" in d else None)
@@ -83,6 +90,11 @@ def setup_replicated(p: Params, seed: int, device_index: int, rank: int, world: 
             s.upload_common(crs.data_ptr())
         del parties, crs
     s.finalize()
+    if timings:
+        nparties = p.k if p.is_mk else 1
+        nbytes = nparties * sum(int(np.prod(shape)) * np.dtype(dt).itemsize for _, shape, dt in key_arrays(p))
+        return s, ks, {"keygen_s": t1 - t0, "broadcast_s": (t2 - t1) if world > 1 else 0.0, "upload_finalize_s": time.perf_counter() - t2,
+                       "key_bytes": nbytes, "note": "rank 0 generates (host, OpenMP); NCCL broadcast GPU->GPU; upload = device-to-device copy + FAST layouts"}
     return s, ks
 
 
