@@ -14,8 +14,8 @@
  *   - Every function returns 0 on success or a negative mktfhe_status; mktfhe_last_error() gives text.
  *     No exception crosses the boundary and the library never calls back into the host language.
  *   - One context belongs to one device and is used from one host thread at a time.  Multi-GPU = one
- *     context per device (one process per GPU under torchrun, or one per device inside one process);
- *     gates are independent, so the caller shards the batch and no collective is involved.
+ *     context per device (one process per GPU under torchrun), or ONE front context over several devices
+ *     (mktfhe_ctx_create_multi) that shards every batch itself; gates are independent, no collective is involved.
  *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
  *     MKTFHE_ERR_CUDA.
  *
@@ -66,6 +66,16 @@ enum mktfhe_mode { MKTFHE_MODE_STRICT = 0, MKTFHE_MODE_FAST = 1 };
 /* ---- lifetime -------------------------------------------------------------------------------- */
 /* Replaces: scheme construction in `setup` (scheme.jl:151-166,190-205,244-252,292-299,343-350). */
 int mktfhe_ctx_create(const mktfhe_params *params, int device, mktfhe_ctx **out);
+/* Multi-GPU in ONE process behind the same entry points: a front context over `ndev` devices
+ * (devices == NULL: 0 .. ndev-1; ndev <= 0: every visible device).  mktfhe_upload_party_key / mktfhe_upload_common copy the
+ * keys host -> first device once; mktfhe_finalize_keys replicates them device to device (cudaMemcpyPeer over NVLink) and
+ * builds tables and FAST layouts on every device; mktfhe_gate_batch / mktfhe_bootstrap_batch cut the host batch into
+ * contiguous slices, one per device, each run from its own host thread on its own stream (results are bit-identical to the
+ * single-device call: gates are independent).  Parity hooks, the wire table and the _dev entry point stay single-device.
+ * The only parallelism the reference has is Threads.@threads over parties (bootstrapping.jl:376-378,573). */
+int mktfhe_ctx_create_multi(const mktfhe_params *params, int ndev, const int *devices, mktfhe_ctx **out);
+/* Number of devices behind ctx (1 for a plain context); fills devices_out[0 .. min(n, cap)). */
+int mktfhe_ctx_devices(const mktfhe_ctx *ctx, int *devices_out, int cap);
 void mktfhe_ctx_destroy(mktfhe_ctx *ctx);
 const char *mktfhe_last_error(const mktfhe_ctx *ctx);   /* ctx may be NULL: last creation error */
 int mktfhe_set_mode(mktfhe_ctx *ctx, int mode);

@@ -18,6 +18,7 @@ EXPORTS = [
     "mktfhe_keyswitch_batch", "mktfhe_cmux_step_batch", "mktfhe_block_step_batch", "mktfhe_fft_batch", "mktfhe_ifft_batch",
     "mktfhe_decomp_batch", "mktfhe_last_stage_ms", "mktfhe_measure_dfma_peak",
     "mktfhe_wires_resize", "mktfhe_wires_write", "mktfhe_wires_read", "mktfhe_gate_level",
+    "mktfhe_ctx_create_multi", "mktfhe_ctx_devices",
 ]
 
 
@@ -32,6 +33,8 @@ def lib() -> ctypes.CDLL:
     L = ctypes.CDLL(path)
     vp, i32, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
     L.mktfhe_ctx_create.argtypes = [ctypes.POINTER(CParams), i32, ctypes.POINTER(vp)]
+    L.mktfhe_ctx_create_multi.argtypes = [ctypes.POINTER(CParams), i32, vp, ctypes.POINTER(vp)]
+    L.mktfhe_ctx_devices.argtypes = [vp, vp, i32]
     L.mktfhe_ctx_destroy.argtypes = [vp]
     L.mktfhe_ctx_destroy.restype = None
     L.mktfhe_last_error.argtypes = [vp]

@@ -56,8 +56,10 @@ def build_host(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in HOST_SRCS]
     deps = srcs + [os.path.join(INCLUDE, h) for h in ("mktfhe_host.h", "mktfhe_params.h")]
     if force or _stale(HOST_LIB, deps):
+        tmp = HOST_LIB + ".tmp"
         _run(["g++", "-O2", "-march=x86-64-v3", "-std=gnu++17", "-fopenmp", "-fPIC", "-shared", "-Wall",
-              "-o", HOST_LIB] + srcs + ["-lquadmath"])
+              "-o", tmp] + srcs + ["-lquadmath"])
+        os.replace(tmp, HOST_LIB)            # atomic: a repo snapshot never sees a half-written library
     return HOST_LIB
 
 
@@ -74,8 +76,10 @@ def build_cuda(force: bool = False) -> str:
     deps = srcs + [os.path.join(CSRC, d) for d in CUDA_DEPS] + \
         [os.path.join(INCLUDE, h) for h in ("mktfhe_b200.h", "mktfhe_params.h")]
     if force or _stale(CUDA_LIB, deps):
-        _run([nvcc_path()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", CUDA_LIB] + srcs + ["-lquadmath"],
+        tmp = CUDA_LIB + ".tmp"
+        _run([nvcc_path()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", tmp] + srcs + ["-lquadmath"],
              log=os.path.join(LIBDIR, "nvcc_build.log"))
+        os.replace(tmp, CUDA_LIB)
     return CUDA_LIB
 
 

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 #include <quadmath.h>
 
@@ -56,6 +57,8 @@ struct mktfhe_ctx {
     int launches = 0;
     std::string err;
     size_t mem_budget = (size_t)24 << 30;
+    // multi-device front (mktfhe_ctx_create_multi): one child context per device, this object only dispatches
+    std::vector<mktfhe_ctx *> children;
 
     FftTables tables() const { return FftTables{psi, psiinv, roots, rootsinv}; }
 };
@@ -372,6 +375,60 @@ template <class T> int decomp_hook(mktfhe_ctx *ctx, int l, int logB, const void 
     return 0;
 }
 
+// ---- multi-device front --------------------------------------------------------------------------------
+// Gates are independent: a front context owns one child per device, keys are uploaded once to the first device
+// and replicated device-to-device, a host batch is cut into contiguous slices and every child runs its slice on its own
+// stream from its own host thread.  No collective on the hot path.
+bool is_multi(const mktfhe_ctx *c) { return c && !c->children.empty(); }
+
+void shard(size_t batch, size_t ndev, size_t r, size_t *lo, size_t *hi) {
+    const size_t base = batch / ndev, rem = batch % ndev;
+    *lo = r * base + (r < rem ? r : rem);
+    *hi = *lo + base + (r < rem ? 1 : 0);
+}
+
+template <class F> int on_children(mktfhe_ctx *front, F fn) {
+    const size_t n = front->children.size();
+    std::vector<int> rcs(n, 0);
+    std::vector<std::thread> th;
+    for (size_t r = 1; r < n; r++) th.emplace_back([&, r]() { rcs[r] = fn(front->children[r], r); });
+    rcs[0] = fn(front->children[0], 0);
+    for (auto &t : th) t.join();
+    for (size_t r = 0; r < n; r++)
+        if (rcs[r]) { front->err = "device " + std::to_string(front->children[r]->device) + ": " + front->children[r]->err; return rcs[r]; }
+    return 0;
+}
+
+template <class T> int clone_buf(mktfhe_ctx *ctx, T *&dst, const T *src, int src_dev, size_t bytes) {
+    dfree(dst);
+    if (!src) return 0;
+    CK(cudaMalloc(&dst, bytes));
+    CK(cudaMemcpyPeer(dst, ctx->device, src, src_dev, bytes));
+    return 0;
+}
+
+// replicate the uploaded (not yet finalized) key material of `src` into `ctx` over NVLink / PCIe peer copies
+int clone_keys(mktfhe_ctx *ctx, const mktfhe_ctx *src) {
+    CK(cudaSetDevice(ctx->device));
+    const mktfhe_params &p = ctx->p;
+    int rc;
+    const size_t rows = (size_t)ctx->N * mktfhe_ksk_rows(&p) * p.f, rowp = ((size_t)p.n + 1 + 3) / 4 * 4;
+    for (int i = 0; i < ctx->nparties; i++) {
+        if ((rc = clone_buf(ctx, ctx->brk[i], src->brk[i], src->device, mktfhe_brk_doubles(&p) * 8))) return rc;
+        if ((rc = clone_buf(ctx, ctx->ksk[i], src->ksk[i], src->device, rows * rowp * 4))) return rc;
+        if ((rc = clone_buf(ctx, ctx->rlk[i], src->rlk[i], src->device, mktfhe_rlk_doubles(&p) * 8))) return rc;
+        if ((rc = clone_buf(ctx, ctx->pubb[i], src->pubb[i], src->device, mktfhe_pubb_doubles(&p) * 8))) return rc;
+    }
+    if ((rc = clone_buf(ctx, ctx->crs, src->crs, src->device, mktfhe_crs_doubles(&p) * 8))) return rc;
+    ctx->finalized = false;
+    return 0;
+}
+
+#define SINGLE_ONLY(ctx, what)                                                                                         \
+    do {                                                                                                               \
+        if (is_multi(ctx)) return fail(ctx, MKTFHE_ERR_ARG, what " is a single-device entry point: use one of the per-device contexts"); \
+    } while (0)
+
 }  // namespace
 
 extern "C" {
@@ -431,8 +488,59 @@ int mktfhe_ctx_create(const mktfhe_params *params, int device, mktfhe_ctx **out)
     return 0;
 }
 
+int mktfhe_ctx_create_multi(const mktfhe_params *params, int ndev, const int *devices, mktfhe_ctx **out) {
+    if (!params || !out) return fail(nullptr, MKTFHE_ERR_ARG, "null argument");
+    *out = nullptr;
+    int avail = 0;
+    cudaError_t e = cudaGetDeviceCount(&avail);
+    if (e != cudaSuccess || avail == 0)
+        return fail(nullptr, MKTFHE_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (ndev <= 0) ndev = avail;
+    std::vector<int> devs(ndev);
+    for (int i = 0; i < ndev; i++) {
+        devs[i] = devices ? devices[i] : i;
+        if (devs[i] < 0 || devs[i] >= avail) return fail(nullptr, MKTFHE_ERR_ARG, "bad device index " + std::to_string(devs[i]));
+        for (int j = 0; j < i; j++) if (devs[j] == devs[i]) return fail(nullptr, MKTFHE_ERR_ARG, "device listed twice");
+    }
+    mktfhe_ctx *front = new mktfhe_ctx;
+    front->p = *params; front->device = devs[0];
+    for (int i = 0; i < ndev; i++) {
+        mktfhe_ctx *child = nullptr;
+        const int rc = mktfhe_ctx_create(params, devs[i], &child);
+        if (rc) { for (auto *c : front->children) mktfhe_ctx_destroy(c); delete front; return rc; }
+        front->children.push_back(child);
+    }
+    // peer access from every device to the first one (key replication); failure only means staged copies
+    for (int i = 1; i < ndev; i++) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, devs[i], devs[0]) == cudaSuccess && can) {
+            cudaSetDevice(devs[i]);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(devs[0], 0);
+            if (pe != cudaSuccess) cudaGetLastError();            // already enabled is fine
+        }
+    }
+    const mktfhe_ctx *c0 = front->children[0];
+    front->N = c0->N; front->H = c0->H; front->bits = c0->bits; front->R = c0->R; front->nparties = c0->nparties;
+    front->mk = c0->mk; front->kms = c0->kms; front->block = c0->block;
+    *out = front;
+    return 0;
+}
+
+int mktfhe_ctx_devices(const mktfhe_ctx *ctx, int *devices_out, int cap) {
+    if (!ctx) return MKTFHE_ERR_ARG;
+    if (!is_multi(ctx)) { if (devices_out && cap > 0) devices_out[0] = ctx->device; return 1; }
+    const int n = (int)ctx->children.size();
+    for (int i = 0; i < n && i < cap && devices_out; i++) devices_out[i] = ctx->children[i]->device;
+    return n;
+}
+
 void mktfhe_ctx_destroy(mktfhe_ctx *ctx) {
     if (!ctx) return;
+    if (is_multi(ctx)) {
+        for (auto *c : ctx->children) mktfhe_ctx_destroy(c);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     free_workspace(ctx);
@@ -454,13 +562,19 @@ void mktfhe_ctx_destroy(mktfhe_ctx *ctx) {
 int mktfhe_set_mode(mktfhe_ctx *ctx, int mode) {
     if (!ctx) return MKTFHE_ERR_ARG;
     if (mode != MKTFHE_MODE_STRICT && mode != MKTFHE_MODE_FAST) return fail(ctx, MKTFHE_ERR_ARG, "bad mode");
+    for (auto *c : ctx->children) c->mode = mode;
     ctx->mode = mode;
     return 0;
 }
-int mktfhe_get_mode(const mktfhe_ctx *ctx) { return ctx ? ctx->mode : MKTFHE_ERR_ARG; }
+int mktfhe_get_mode(const mktfhe_ctx *ctx) { return ctx ? (is_multi(ctx) ? ctx->children[0]->mode : ctx->mode) : MKTFHE_ERR_ARG; }
 
 int mktfhe_upload_party_key(mktfhe_ctx *ctx, int party, const double *brk, const double *rlk, const double *pubb, const uint32_t *ksk) {
     if (!ctx) return MKTFHE_ERR_ARG;
+    if (is_multi(ctx)) {            // one host -> device copy; mktfhe_finalize_keys replicates device to device
+        const int rc = mktfhe_upload_party_key(ctx->children[0], party, brk, rlk, pubb, ksk);
+        if (rc) ctx->err = ctx->children[0]->err;
+        return rc;
+    }
     if (party < 0 || party >= ctx->nparties) return fail(ctx, MKTFHE_ERR_ARG, "bad party index");
     if (!brk || !ksk) return fail(ctx, MKTFHE_ERR_ARG, "brk and ksk are required");
     if (ctx->kms && (!rlk || !pubb)) return fail(ctx, MKTFHE_ERR_ARG, "KMS needs rlk and pubb");
@@ -483,6 +597,11 @@ int mktfhe_upload_party_key(mktfhe_ctx *ctx, int party, const double *brk, const
 
 int mktfhe_upload_common(mktfhe_ctx *ctx, const double *crs_fft) {
     if (!ctx) return MKTFHE_ERR_ARG;
+    if (is_multi(ctx)) {
+        const int rc = mktfhe_upload_common(ctx->children[0], crs_fft);
+        if (rc) ctx->err = ctx->children[0]->err;
+        return rc;
+    }
     if (!ctx->mk) return 0;
     if (!crs_fft) return fail(ctx, MKTFHE_ERR_ARG, "crs_fft is required for CCS / KMS");
     CK(cudaSetDevice(ctx->device));
@@ -492,6 +611,18 @@ int mktfhe_upload_common(mktfhe_ctx *ctx, const double *crs_fft) {
 
 int mktfhe_finalize_keys(mktfhe_ctx *ctx) {
     if (!ctx) return MKTFHE_ERR_ARG;
+    if (is_multi(ctx)) {
+        // replicate (peer copies from the first device, one thread per target), then build tables and FAST layouts everywhere
+        const int rc = on_children(ctx, [&](mktfhe_ctx *c, size_t r) -> int {
+            if (r > 0) { const int rc2 = clone_keys(c, ctx->children[0]); if (rc2) return rc2; }
+            return 0;
+        });
+        if (rc) return rc;
+        const int rc3 = on_children(ctx, [&](mktfhe_ctx *c, size_t) -> int { return mktfhe_finalize_keys(c); });
+        if (rc3) return rc3;
+        ctx->mode = ctx->children[0]->mode; ctx->finalized = true;
+        return 0;
+    }
     CK(cudaSetDevice(ctx->device));
     for (int i = 0; i < ctx->nparties; i++)
         if (!ctx->brk[i] || !ctx->ksk[i]) return fail(ctx, MKTFHE_ERR_STATE, "party key missing: " + std::to_string(i));
@@ -534,12 +665,13 @@ int mktfhe_finalize_keys(mktfhe_ctx *ctx) {
 
 int mktfhe_sync(mktfhe_ctx *ctx) {
     if (!ctx) return MKTFHE_ERR_ARG;
+    if (is_multi(ctx)) return on_children(ctx, [](mktfhe_ctx *c, size_t) -> int { return mktfhe_sync(c); });
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
-void *mktfhe_stream(mktfhe_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+void *mktfhe_stream(mktfhe_ctx *ctx) { return ctx ? (void *)(is_multi(ctx) ? ctx->children[0]->stream : ctx->stream) : nullptr; }
 
 static int run_pipeline(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2, uint32_t *out, size_t g,
                         const int32_t *ops = nullptr, const int32_t *idx1 = nullptr, const int32_t *idx2 = nullptr) {
@@ -558,6 +690,8 @@ static int run_pipeline(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const
 
 int mktfhe_gate_batch_dev(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2, uint32_t *out, size_t batch) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_gate_batch_dev");
     if ((rc = check_ready(ctx))) return rc;
     if (!in1 || !out || (gate_op >= 0 && !in2)) return fail(ctx, MKTFHE_ERR_ARG, "null ciphertext pointer");
     if (gate_op > MKTFHE_NOR) return fail(ctx, MKTFHE_ERR_ARG, "bad gate opcode");
@@ -575,6 +709,19 @@ int mktfhe_gate_batch_dev(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, con
 
 int mktfhe_gate_batch(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2, uint32_t *out, size_t batch) {
     int rc;
+    if (is_multi(ctx)) {
+        if (!ctx->finalized) return fail(ctx, MKTFHE_ERR_STATE, "keys not finalized: call mktfhe_finalize_keys first");
+        if (!in1 || !out || (gate_op >= 0 && !in2)) return fail(ctx, MKTFHE_ERR_ARG, "null ciphertext pointer");
+        if (gate_op > MKTFHE_NOR) return fail(ctx, MKTFHE_ERR_ARG, "bad gate opcode");
+        const size_t lw = mktfhe_lwe_words(&ctx->p), nd = ctx->children.size();
+        // contiguous slices of the caller's arrays, one per device, each on its own host thread and stream
+        return on_children(ctx, [&](mktfhe_ctx *c, size_t r) -> int {
+            size_t lo, hi;
+            shard(batch, nd, r, &lo, &hi);
+            if (hi == lo) { c->events_used = 0; c->launches = 0; return 0; }
+            return mktfhe_gate_batch(c, gate_op, in1 + lo * lw, in2 ? in2 + lo * lw : nullptr, out + lo * lw, hi - lo);
+        });
+    }
     if ((rc = check_ready(ctx))) return rc;
     if (!in1 || !out || (gate_op >= 0 && !in2)) return fail(ctx, MKTFHE_ERR_ARG, "null ciphertext pointer");
     if (gate_op > MKTFHE_NOR) return fail(ctx, MKTFHE_ERR_ARG, "bad gate opcode");
@@ -601,6 +748,19 @@ int mktfhe_bootstrap_batch(mktfhe_ctx *ctx, const uint32_t *in, uint32_t *out, s
 
 int mktfhe_last_stage_ms(mktfhe_ctx *ctx, float *ms_out, int *launches_out) {
     if (!ctx || !ms_out) return MKTFHE_ERR_ARG;
+    if (is_multi(ctx)) {            // slowest device per stage, launches summed
+        for (int s = 0; s < MKTFHE_STAGE_COUNT; s++) ms_out[s] = 0.f;
+        int total = 0;
+        for (auto *c : ctx->children) {
+            float ms[MKTFHE_STAGE_COUNT]; int l = 0;
+            const int rc = mktfhe_last_stage_ms(c, ms, &l);
+            if (rc) { ctx->err = c->err; return rc; }
+            for (int s = 0; s < MKTFHE_STAGE_COUNT; s++) ms_out[s] = std::max(ms_out[s], ms[s]);
+            total += l;
+        }
+        if (launches_out) *launches_out = total;
+        return 0;
+    }
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int s = 0; s < MKTFHE_STAGE_COUNT; s++) ms_out[s] = 0.f;
@@ -618,6 +778,8 @@ int mktfhe_last_stage_ms(mktfhe_ctx *ctx, float *ms_out, int *launches_out) {
 
 int mktfhe_wires_resize(mktfhe_ctx *ctx, size_t nwires) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_wires_resize");
     if ((rc = check_ready(ctx))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     dfree(ctx->wires);
@@ -633,6 +795,8 @@ int mktfhe_wires_resize(mktfhe_ctx *ctx, size_t nwires) {
 
 int mktfhe_wires_write(mktfhe_ctx *ctx, size_t first, size_t count, const uint32_t *cts) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_wires_write");
     if ((rc = check_ready(ctx))) return rc;
     if (first + count > ctx->nwires || first + count < first) return fail(ctx, MKTFHE_ERR_ARG, "wire range outside the table");
     if (count == 0) return 0;
@@ -645,6 +809,8 @@ int mktfhe_wires_write(mktfhe_ctx *ctx, size_t first, size_t count, const uint32
 
 int mktfhe_wires_read(mktfhe_ctx *ctx, size_t first, size_t count, uint32_t *cts) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_wires_read");
     if ((rc = check_ready(ctx))) return rc;
     if (first + count > ctx->nwires || first + count < first) return fail(ctx, MKTFHE_ERR_ARG, "wire range outside the table");
     if (count == 0) return 0;
@@ -657,6 +823,8 @@ int mktfhe_wires_read(mktfhe_ctx *ctx, size_t first, size_t count, uint32_t *cts
 
 int mktfhe_gate_level(mktfhe_ctx *ctx, const int32_t *ops, const int32_t *src1, const int32_t *src2, const int32_t *dst, size_t batch) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_gate_level");
     if ((rc = check_ready(ctx))) return rc;
     if (batch == 0) return 0;
     if (!ops || !src1 || !src2 || !dst) return fail(ctx, MKTFHE_ERR_ARG, "null index array");
@@ -716,6 +884,8 @@ int mktfhe_gate_level(mktfhe_ctx *ctx, const int32_t *ops, const int32_t *src1, 
 
 int mktfhe_gate_linear_batch(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const uint32_t *in2, uint32_t *out, size_t batch) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_gate_linear_batch");
     if ((rc = check_ready(ctx))) return rc;
     if (!in1 || !in2 || !out || gate_op < 0 || gate_op > MKTFHE_NOR) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
     const size_t lw = mktfhe_lwe_words(&ctx->p);
@@ -730,6 +900,8 @@ int mktfhe_gate_linear_batch(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, 
 
 int mktfhe_modswitch_batch(mktfhe_ctx *ctx, const uint32_t *lwe, uint32_t *tilde, size_t batch) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_modswitch_batch");
     if ((rc = check_ready(ctx))) return rc;
     if (!lwe || !tilde) return fail(ctx, MKTFHE_ERR_ARG, "null pointer");
     const size_t lw = mktfhe_lwe_words(&ctx->p);
@@ -743,6 +915,8 @@ int mktfhe_modswitch_batch(mktfhe_ctx *ctx, const uint32_t *lwe, uint32_t *tilde
 
 int mktfhe_blindrotate_batch(mktfhe_ctx *ctx, const uint32_t *lwe, void *acc_out, size_t batch) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_blindrotate_batch");
     if ((rc = check_ready(ctx))) return rc;
     if (!lwe || !acc_out) return fail(ctx, MKTFHE_ERR_ARG, "null pointer");
     const size_t lw = mktfhe_lwe_words(&ctx->p);
@@ -757,6 +931,8 @@ int mktfhe_blindrotate_batch(mktfhe_ctx *ctx, const uint32_t *lwe, void *acc_out
 
 int mktfhe_phase1_batch(mktfhe_ctx *ctx, const uint32_t *lwe, double *levkeys_out, size_t batch) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_phase1_batch");
     if ((rc = check_ready(ctx))) return rc;
     if (!ctx->kms) return fail(ctx, MKTFHE_ERR_PARAMS, "phase 1 exists for KMS / KMS_BLOCK only");
     if (!lwe || !levkeys_out) return fail(ctx, MKTFHE_ERR_ARG, "null pointer");
@@ -772,6 +948,8 @@ int mktfhe_phase1_batch(mktfhe_ctx *ctx, const uint32_t *lwe, double *levkeys_ou
 
 int mktfhe_keyswitch_batch(mktfhe_ctx *ctx, const void *acc, uint32_t *lwe_out, size_t batch) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_keyswitch_batch");
     if ((rc = check_ready(ctx))) return rc;
     if (!acc || !lwe_out) return fail(ctx, MKTFHE_ERR_ARG, "null pointer");
     const size_t lw = mktfhe_lwe_words(&ctx->p);
@@ -785,6 +963,8 @@ int mktfhe_keyswitch_batch(mktfhe_ctx *ctx, const void *acc, uint32_t *lwe_out, 
 
 static int step_impl(mktfhe_ctx *ctx, int party, int idx, const uint32_t *atilde, void *acc_rows, size_t batch, bool block_step) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_cmux_step_batch / mktfhe_block_step_batch");
     if ((rc = check_ready(ctx))) return rc;
     if (ctx->p.scheme == MKTFHE_CCS) return fail(ctx, MKTFHE_ERR_PARAMS, "CCS has no RGSW step");
     if (block_step && !ctx->block) return fail(ctx, MKTFHE_ERR_PARAMS, "block step needs LMSS / KMS_BLOCK");
@@ -825,6 +1005,8 @@ int mktfhe_block_step_batch(mktfhe_ctx *ctx, int party, int blk, const uint32_t 
 
 int mktfhe_fft_batch(mktfhe_ctx *ctx, int bits, const void *polys, double *spectra, size_t batch) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_fft_batch");
     if ((rc = check_ready(ctx))) return rc;
     if (!polys || !spectra || (bits != 32 && bits != 64)) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
     return bits == 64 ? fft_hook<uint64_t>(ctx, false, polys, spectra, batch) : fft_hook<uint32_t>(ctx, false, polys, spectra, batch);
@@ -832,6 +1014,8 @@ int mktfhe_fft_batch(mktfhe_ctx *ctx, int bits, const void *polys, double *spect
 
 int mktfhe_ifft_batch(mktfhe_ctx *ctx, int bits, const double *spectra, void *polys, size_t batch) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_ifft_batch");
     if ((rc = check_ready(ctx))) return rc;
     if (!polys || !spectra || (bits != 32 && bits != 64)) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
     return bits == 64 ? fft_hook<uint64_t>(ctx, true, spectra, polys, batch) : fft_hook<uint32_t>(ctx, true, spectra, polys, batch);
@@ -839,6 +1023,8 @@ int mktfhe_ifft_batch(mktfhe_ctx *ctx, int bits, const double *spectra, void *po
 
 int mktfhe_decomp_batch(mktfhe_ctx *ctx, int bits, int l, int logB, const void *polys, void *digits, size_t batch) {
     int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_decomp_batch");
     if ((rc = check_ready(ctx))) return rc;
     if (!polys || !digits || (bits != 32 && bits != 64) || l < 1 || l > MK_MAXL * 2 || logB < 1 || l * logB > bits)
         return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
@@ -847,6 +1033,7 @@ int mktfhe_decomp_batch(mktfhe_ctx *ctx, int bits, int l, int logB, const void *
 
 int mktfhe_measure_dfma_peak(mktfhe_ctx *ctx, double *tflops_out) {
     if (!ctx || !tflops_out) return MKTFHE_ERR_ARG;
+    if (is_multi(ctx)) return mktfhe_measure_dfma_peak(ctx->children[0], tflops_out);
     CK(cudaSetDevice(ctx->device));
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));

@@ -10,14 +10,16 @@
 //     shared-memory exchange traffic -- the L1/shared data pipe was 59 % busy next to an FP64 pipe at 58 % -- removes
 //     every barrier from the transforms and doubles the independent butterflies per stage (32 chains).
 //   * A unit = one (gate, party, RLEV row) still owns one TMEM lane quadrant (64 KiB: RLWE accumulator + RGSW
-//     accumulators), shared by TWO warps q and q + 4 (same quadrant, same scheduler).  The 2l gadget digits of a step
-//     alternate between them: warp A transforms digits 0, 2, 4, ..., warp B digits 1, 3, 5, ...; each multiplies its
-//     spectrum into the shared RGSW accumulators when it holds the token (named-barrier arrive / sync pairs, strictly
-//     alternating A, B, A, ...), so the accumulation order over the digits is the sequential one.  Then A inverse-
-//     transforms the .b output and B the .a output, each updates its half of the RLWE accumulator, and one 64-thread
-//     barrier closes the step.  Per step and unit: 2l token hand-offs + 1 barrier instead of 32 blocking barriers.
-//   * Bootstrapping-key tiles arrive once per CTA through the same cp.async.bulk + mbarrier ring as before; a tile is
-//     consumed by the one warp per unit that owns its digit (one elected lane per warp releases the slot).
+//     accumulators), shared by TWO warps q and q + 4 (same quadrant, same scheduler).  Warp A owns the .b half of the RLWE
+//     accumulator: it decomposes and transforms the l gadget digits of acc.b, inverse-transforms the .b sum and updates
+//     acc.b.  Warp B does the same for acc.a.  Every spectrum must be multiplied into BOTH sums, so per digit A adds into
+//     the .b sum first and the .a sum second while B goes .a first, .b second: the two warps always work on opposite
+//     sums, and four mbarrier tokens per unit (b: A->B, B->A; a: B->A, A->B) fix the order of the additions
+//     (.b: A0, B0, A1, B1, ...; .a: B0, A0, B1, A1, ...), so results are deterministic.  Nothing else couples the warps:
+//     no block barrier inside the step loop (the 64-thread mapping needed 32 per step).
+//   * Bootstrapping-key tiles arrive once per CTA through the same cp.async.bulk + mbarrier ring as before, in the order the
+//     warps consume them (A_j.b, B_j.a, A_j.a, B_j.b); a tile is consumed by one warp per unit (one elected lane per warp
+//     releases the slot).  All mbarrier waits suspend in hardware (try_wait with a time hint) instead of spinning.
 //
 // Index math of the transform is modelled and checked against the oracle in tools/models/fft32_model.py.
 #pragma once
@@ -37,7 +39,7 @@ constexpr int XBW = H + 32;                 // exchange buffer: element n at n +
 constexpr int RINGW = 5;                    // key tiles (16 KiB polynomials) in flight
 constexpr int W_LAUNCH_REGS = 168, W_CONSUMER_REGS = 232, W_PRODUCER_REGS = 24;
 static_assert(NCW * W_CONSUMER_REGS + 4 * W_PRODUCER_REGS <= (CTA_W / 32) * W_LAUNCH_REGS, "setmaxnreg over-subscription");
-constexpr size_t SMEM_BYTES_W = ((size_t)NCW * XBW + 512 + (size_t)RINGW * H) * 16 + 2 * RINGW * 8 + 16;
+constexpr size_t SMEM_BYTES_W = ((size_t)NCW * XBW + 512 + (size_t)RINGW * H) * 16 + (2 * RINGW + 4 * WU) * 8 + 16;
 static_assert(SMEM_BYTES_W <= 232448, "shared memory budget");
 
 __constant__ double2 c_tw1w[32];     // TW[1..31]: stages 1..5 (index 2^s + node), entry 0 unused
@@ -140,13 +142,30 @@ __device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0,
 __device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// producer-side wait: back off between polls so that the spin does not take issue slots from the compute warps of its scheduler
+// mbarrier wait that suspends the thread in hardware until the phase completes (or the hint expires) instead of spinning: the
+// polling loop of the producer took a quarter of its scheduler's issue slots (highest warp id wins arbitration).  Bounded: a
+// protocol error traps after ~1 s instead of hanging the device.
+__device__ __forceinline__ bool mb_try_hint(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+                 "selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mb_wait_sleep(uint64_t *bar, uint32_t parity) {
     uint32_t spins = 0;
-    while (!fast::mb_try(bar, parity)) {
-        __nanosleep(64);
-        if (++spins > (1u << 24)) __trap();
-    }
+    while (!mb_try_hint(bar, parity, 20000u))
+        if (++spins > (1u << 22)) __trap();
+}
+// token = mbarrier with one arrival per phase; the waiter keeps the phase parity
+struct Token {
+    uint64_t *bar;
+    uint32_t par;
+    __device__ __forceinline__ void wait() { mb_wait_sleep(bar, par); par ^= 1; }
+};
+__device__ __forceinline__ void token_pass(uint64_t *bar, int t) {     // all lanes' TMEM stores are complete (tcgen05.wait::st)
+    __syncwarp();
+    if (t == 0) mb_arrive(bar);
 }
 // ring position of a consumer warp: tile -> (slot, phase parity), advanced without divisions
 struct RingPos {
@@ -165,10 +184,12 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
     cplx *tw2s = xb_all + (size_t)NCW * XBW;
     cplx *ring = tw2s + 512;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)RINGW * H), *empty = full + RINGW;
-    uint32_t *tm_base_s = reinterpret_cast<uint32_t *>(empty + RINGW);
+    uint64_t *tokens = empty + RINGW;                               // [WU][4]: b A->B, b B->A, a B->A, a A->B
+    uint32_t *tm_base_s = reinterpret_cast<uint32_t *>(tokens + 4 * WU);
     for (int i = tid; i < 512; i += CTA_W) tw2s[i] = a.tb.t2w[i];
     if (tid == 0) {
         for (int s = 0; s < RINGW; s++) { mb_init(&full[s], 1); mb_init(&empty[s], WU); }
+        for (int s = 0; s < 4 * WU; s++) mb_init(&tokens[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -196,22 +217,30 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
 
     if (warp >= NCW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        // ---- producer: tile n = (step * 2l + dg) * 2 + comp, one 16 KiB polynomial in thread order [e][t]
+        // ---- producer: 16 KiB polynomials in thread order [e][t], in consumption order: per step and j < l the four tiles
+        //      A_j.b = (digit j, .b), B_j.a = (digit l + j, .a), A_j.a = (digit j, .a), B_j.b = (digit l + j, .b)
         if (tid == NCW * 32) {
+            uint32_t slot = 0, par = 1, step = 0, j = 0, r = 0;         // par: parity of the PREVIOUS phase of empty[slot]
             for (uint32_t n = 0; n < ntiles; n++) {
-                const int slot = n % RINGW;
-                if (n >= RINGW) mb_wait_sleep(&empty[slot], ((n / RINGW) - 1) & 1);
-                const uint32_t within = n % (uint32_t)(4 * l), step = n / (uint32_t)(4 * l);
+                if (n >= RINGW) mb_wait_sleep(&empty[slot], par);
+                const uint32_t dg = (r & 1) ? (uint32_t)l + j : j, comp = (r == 1 || r == 2) ? 1u : 0u;
                 const int idx = a.step_mode ? a.step_idx : (int)step;
                 mb_expect_tx(&full[slot], H * 16);
-                bulk_g2s(ring + (size_t)slot * H, brk + (size_t)idx * per_idx + (size_t)within * H, H * 16, &full[slot]);
+                bulk_g2s(ring + (size_t)slot * H, brk + (size_t)idx * per_idx + (size_t)(dg * 2 + comp) * H, H * 16, &full[slot]);
+                if (++slot == RINGW) { slot = 0; par ^= 1; }
+                if (++r == 4) { r = 0; if (++j == (uint32_t)l) { j = 0; step++; } }
             }
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-        // ---- consumers: unit q = TMEM lane quadrant, role w (0: even digits and the .b output, 1: odd digits and .a)
+        // ---- consumers: unit q = TMEM lane quadrant, role w (0 = A: the .b half, 1 = B: the .a half)
         const int q = warp & 3, w = warp >> 2;
-        const int BAR_STEP = 1 + q, BAR_AB = 5 + q, BAR_BA = 9 + q;
+        uint64_t *tk = tokens + 4 * q;
+        // sum I add into FIRST (own) and SECOND (other): tokens I wait on / pass on
+        //   own sum:   wait other's second-pass token of the previous digit, pass my first-pass token
+        //   other sum: wait other's first-pass token of this digit, pass my second-pass token
+        Token wait_own{w == 0 ? &tk[1] : &tk[3], 0u}, wait_oth{w == 0 ? &tk[2] : &tk[0], 0u};
+        uint64_t *pass_own = w == 0 ? &tk[0] : &tk[2], *pass_oth = w == 0 ? &tk[3] : &tk[1];
         const uint32_t tm = *tm_base_s + ((uint32_t)(32 * q) << 16);
         cplx *xb = xb_all + (size_t)warp * XBW;
         const cplx *tw = tw2s + t;
@@ -256,9 +285,6 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                 }
             }
             tm_wait_st();
-            tm_fence_before();
-            nb_sync(BAR_STEP);
-            tm_fence_after();
         }
         const int logB = a.logB;
         const int bit = 64 - l * logB;
@@ -269,20 +295,16 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
         const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));
         const uint32_t *at_src = a.step_mode ? a.tilde + up : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
         const int brv5t = (int)(__brev((unsigned)t) >> 27);
-        // this warp's first tile is 2w (digit w, component .b); it consumes tiles 4j + 2w, 4j + 2w + 1 of every step
-        RingPos rp{(uint32_t)(2 * w) % RINGW, 0u};
+        // this warp consumes every second tile of the producer's sequence, starting at tile w
+        RingPos rp{(uint32_t)w, 0u};
 
         for (int step = 0; step < nsteps; step++) {
             const uint32_t at = live ? at_src[a.step_mode ? 0 : step] : 0u;
             if (at == 0) {                                          // :413 / dead unit: keep the ring moving, compute nothing
-                for (int j = 0; j < l; j++) {
-#pragma unroll
-                    for (int comp = 0; comp < 2; comp++) {
-                        mb_wait(&full[rp.slot], rp.par);
-                        __syncwarp();
-                        if (t == 0) mb_arrive(&empty[rp.slot]);
-                        rp.advance(1);
-                    }
+                for (int j = 0; j < 2 * l; j++) {
+                    mb_wait_sleep(&full[rp.slot], rp.par);
+                    __syncwarp();
+                    if (t == 0) mb_arrive(&empty[rp.slot]);
                     rp.advance(2);
                 }
                 continue;
@@ -290,15 +312,13 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
             const cplx m1 = __ldg(&a.tb.emono[((4 * brv5t + 1) * at) & 4095]);
 
             for (int j = 0; j < l; j++) {
-                const int dg = 2 * j + w;
-                const uint32_t src = tm + (dg < l ? TMW_ACC_B : TMW_ACC_A);
-                const int sh = bit + (l - 1 - (dg < l ? dg : dg - l)) * logB;
+                const int sh = bit + (l - 1 - j) * logB;             // digit j (0 = most significant) of my half of the accumulator
                 cplx x[32];
 #pragma unroll
                 for (int hb = 0; hb < 2; hb++) {                     // gadget digit of 64 coefficients -> 32 complex points
                     uint32_t v[4][16];
 #pragma unroll
-                    for (int c = 0; c < 4; c++) tm_ld16(src + 64 * hb + 16 * c, v[c]);
+                    for (int c = 0; c < 4; c++) tm_ld16(tm_acc + 64 * hb + 16 * c, v[c]);
                     tm_wait_ld();
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
@@ -314,17 +334,15 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                     }
                 }
                 fft_fwd(x, xb, tw, t);
-                if (dg != 0) {                                      // token: the previous digit's products are in TMEM
-                    nb_sync(w == 0 ? BAR_BA : BAR_AB);
-                    tm_fence_after();
-                }
-                // RGSW accumulators += spectrum x key, one output component per pass; the accumulator chunk after the one
-                // being updated is already in flight
+                // RGSW sums += spectrum x key: my own sum first, the other warp's sum second (the other warp goes the other way
+                // round); the accumulator chunk after the one being updated is already in flight
 #pragma unroll
-                for (int pz = 0; pz < 2; pz++) {
-                    mb_wait(&full[rp.slot], rp.par);
+                for (int ps = 0; ps < 2; ps++) {
+                    const uint32_t tmz = ps == 0 ? tm_tacc : tm + (w == 0 ? TMW_TACC_A : TMW_TACC_B);
+                    mb_wait_sleep(&full[rp.slot], rp.par);
                     const cplx *kp = ring + (size_t)rp.slot * H + t;
-                    const uint32_t tmz = tm + (pz == 0 ? TMW_TACC_B : TMW_TACC_A);
+                    if (ps == 0) { if (j > 0) wait_own.wait(); } else wait_oth.wait();
+                    tm_fence_after();
                     uint32_t v[2][16];
                     tm_ld16(tmz, v[0]);
 #pragma unroll
@@ -339,19 +357,15 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                         for (int i = 0; i < 4; i++) z[i] = cmac_f(unpack_c(v[c & 1], i), x[4 * c + i], kc[i]);
                         tm_st_c4(tmz + 16 * c, z);
                     }
-                    __syncwarp();
-                    if (t == 0) mb_arrive(&empty[rp.slot]);         // this key tile is done
-                    rp.advance(1);
+                    tm_wait_st();
+                    tm_fence_before();
+                    token_pass(ps == 0 ? pass_own : pass_oth, t);      // also orders every lane's key reads before the release below
+                    if (t == 0) mb_arrive(&empty[rp.slot]);             // this key tile is done
+                    rp.advance(2);
                 }
-                rp.advance(2);                                      // skip the other warp's digit
-                tm_wait_st();
-                tm_fence_before();
-                nb_arrive(w == 0 ? BAR_AB : BAR_BA);                // pass the token
             }
-            if (w == 0) {                                           // B's last product closes the sums
-                nb_sync(BAR_BA);
-                tm_fence_after();
-            }
+            wait_own.wait();                                        // the other warp's last addition into my sum
+            tm_fence_after();
             // this warp's output: (x (X^a - 1)/H) -> inverse transform -> round -> acc +=
             {
                 cplx y[32];
@@ -403,9 +417,6 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                 }
                 tm_wait_st();
             }
-            tm_fence_before();
-            nb_sync(BAR_STEP);                                      // both halves of the accumulator are updated, the sums are clear
-            tm_fence_after();
         }
 
         if (live) {

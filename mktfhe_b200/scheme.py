@@ -29,13 +29,28 @@ def _ptr(a):
 class Scheme:
     """One device context holding the uploaded evaluation keys of every party."""
 
-    def __init__(self, params: Params, device: int = 0):
+    def __init__(self, params: Params, device: int = 0, devices=None):
+        """device: one GPU.  devices: a list of GPUs (or "all") behind ONE front context (mktfhe_ctx_create_multi): keys are
+        replicated device to device at finalize() and every gate / bootstrapping batch is sharded in contiguous slices."""
         self.params = params
-        self.device = device
         self._h = ctypes.c_void_p()
         L = _lib.lib()
         cp = params.c_struct()
-        rc = L.mktfhe_ctx_create(ctypes.byref(cp), device, ctypes.byref(self._h))
+        if devices is None:
+            self.device, self.devices = device, [device]
+            rc = L.mktfhe_ctx_create(ctypes.byref(cp), device, ctypes.byref(self._h))
+        else:
+            if isinstance(devices, str):
+                arr, n = None, 0
+            else:
+                devs = [int(d) for d in devices]
+                arr, n = (ctypes.c_int * len(devs))(*devs), len(devs)
+            rc = L.mktfhe_ctx_create_multi(ctypes.byref(cp), n, arr, ctypes.byref(self._h))
+            if rc == 0:
+                out = (ctypes.c_int * 64)()
+                cnt = L.mktfhe_ctx_devices(self._h, out, 64)
+                self.devices = [out[i] for i in range(cnt)]
+                self.device = self.devices[0]
         if rc != 0:
             raise MktfheError(f"mktfhe_ctx_create: {rc}: {L.mktfhe_last_error(None).decode()}")
 
@@ -229,10 +244,11 @@ class Scheme:
         return v.value
 
 
-def setup(keys: KeySet, device: int = 0, mode: int | None = None) -> Scheme:
-    """`scheme = setup(a, btk, params)` / `setup(params)`: create the device context and upload every party's keys."""
+def setup(keys: KeySet, device: int = 0, mode: int | None = None, devices=None) -> Scheme:
+    """`scheme = setup(a, btk, params)` / `setup(params)`: create the device context and upload every party's keys.
+    devices=[0, 1, ...] (or "all"): one front context over several GPUs of this process."""
     p = keys.params
-    s = Scheme(p, device)
+    s = Scheme(p, device, devices)
     for i, q in enumerate(keys.parties):
         s.upload_party(i, q["brk"], q["ksk"], q["rlk"], q["pubb"])
     if p.is_mk:

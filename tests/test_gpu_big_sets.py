@@ -125,7 +125,10 @@ def test_fast_vs_strict_decrypt_and_noise(gpu_schemes, name):
     s.set_mode(MODE_FAST)
     (ok_s, sd_s), (ok_f, sd_f) = stats[MODE_STRICT], stats[MODE_FAST]
     print(f"{name}: STRICT ok {ok_s}/{2 * B} sigma 2^{np.log2(sd_s):.2f}; FAST ok {ok_f}/{2 * B} sigma 2^{np.log2(sd_f):.2f} (margin 2^29)")
-    assert 0.75 < sd_f / sd_s < 1.33
+    # FAST may be LESS noisy than STRICT at k = 32: with the 64-bit torus and beta = 85 the blind-rotation error of these sets is
+    # dominated by Float64 rounding in the transforms (per-step error ~2^31, as large as the RGSW noise itself), and the fused
+    # multiply-add schedule rounds about half as often as the reference's.  Measured on B200: 0.74 at KMS32partyblock.
+    assert 0.6 < sd_f / sd_s < 1.33
     if name in ("CCS16party", "KMS32party", "KMS32partyblock"):
         # at the margin by construction of the parameter set: both modes must show the same failure level
         assert abs(ok_f - ok_s) <= 8 and min(ok_f, ok_s) >= 0.85 * 2 * B
