@@ -891,8 +891,10 @@ __device__ __forceinline__ void mb_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mb_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
-// Bounded spin: a protocol error (a tile nobody releases, a setmaxnreg over-subscription upstream) traps after ~2^26 failed
-// polls (>= 0.5 s; no legitimate wait is longer than a few microseconds) instead of hanging the device until the watchdog.
+// mbarrier wait: try_wait with a suspend-time hint parks the thread in hardware until the phase completes (or the hint expires)
+// instead of spinning -- a spinning producer took a quarter of its scheduler's issue slots (the highest warp id wins
+// arbitration).  Bounded: a protocol error (a tile nobody releases, a setmaxnreg over-subscription upstream) traps after
+// 2^22 expired hints instead of hanging the device until the watchdog.
 __device__ __forceinline__ bool mb_try(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n.reg .pred p;\n"
@@ -900,10 +902,17 @@ __device__ __forceinline__ bool mb_try(uint64_t *bar, uint32_t parity) {
                  "selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mb_try_hint(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+                 "selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mb_wait(uint64_t *bar, uint32_t parity) {
     uint32_t spins = 0;
-    while (!mb_try(bar, parity))
-        if (++spins > (1u << 26)) __trap();
+    while (!mb_try_hint(bar, parity, 20000u))
+        if (++spins > (1u << 22)) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

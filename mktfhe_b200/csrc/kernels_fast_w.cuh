@@ -142,21 +142,7 @@ __device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0,
 __device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// mbarrier wait that suspends the thread in hardware until the phase completes (or the hint expires) instead of spinning: the
-// polling loop of the producer took a quarter of its scheduler's issue slots (highest warp id wins arbitration).  Bounded: a
-// protocol error traps after ~1 s instead of hanging the device.
-__device__ __forceinline__ bool mb_try_hint(uint64_t *bar, uint32_t parity, uint32_t ns) {
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-                 "selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity), "r"(ns) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mb_wait_sleep(uint64_t *bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mb_try_hint(bar, parity, 20000u))
-        if (++spins > (1u << 22)) __trap();
-}
+__device__ __forceinline__ void mb_wait_sleep(uint64_t *bar, uint32_t parity) { fast::mb_wait(bar, parity); }
 // token = mbarrier with one arrival per phase; the waiter keeps the phase parity
 struct Token {
     uint64_t *bar;
