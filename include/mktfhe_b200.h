@@ -90,6 +90,19 @@ int mktfhe_upload_party_key(mktfhe_ctx *ctx, int party, const double *brk, const
                             const double *pubb, const uint32_t *ksk);
 /* Replaces: `fft(a, ffter)` stored as scheme.a (scheme.jl:251,298,349). NULL for CGGI / LMSS. */
 int mktfhe_upload_common(mktfhe_ctx *ctx, const double *crs_fft);
+/* ---- key generation on the device ----------------------------------------------------------------
+ * Replaces: CRS (scheme.jl:409-410) + fft.(a, ffter) and party_keygen's BootKey constructors (keygen.jl:3-155: rgsw_encrypt per
+ * key bit, unienc_encrypt, gen_b, lev_encrypt per ring coefficient) for the case that one process owns the seeds (benchmarks,
+ * tests, a party generating its own keys on its own GPU).  The material is generated from the SAME seeded ChaCha20 streams as
+ * mktfhe_host_party_keygen (include/mktfhe_host.h), with exact integer ring products and the reference's Float64 transform, so
+ * for one seed it is byte-identical to the host library's (tests/test_gpu_keygen.py compares SHA-256) -- and it never crosses
+ * PCIe.  key32 = 32-byte ChaCha20 key (production), or NULL to expand the 64-bit `seed` (reproducible runs).
+ * mktfhe_keygen_common must precede mktfhe_keygen_party for CCS / KMS* (it generates and keeps the CRS); then mktfhe_finalize_keys.
+ * The matching secret keys come from mktfhe_host_party_keygen with all evaluation-key outputs NULL (same seed). */
+int mktfhe_keygen_common(mktfhe_ctx *ctx, uint64_t seed, const uint8_t *key32);
+int mktfhe_keygen_party(mktfhe_ctx *ctx, int party, uint64_t seed, const uint8_t *key32);
+/* Parity hook: copies a party's uploaded or generated keys back in the flat layouts (any pointer may be NULL). */
+int mktfhe_download_party_key(mktfhe_ctx *ctx, int party, double *brk, double *rlk, double *pubb, uint32_t *ksk, double *crs_fft);
 /* Builds the transform tables (fft.jl:26-44) and monomial table (scheme.jl:121-146) on the device and
  * the FAST-mode key layouts.  Must be called once after all uploads. */
 int mktfhe_finalize_keys(mktfhe_ctx *ctx);
@@ -148,6 +161,12 @@ int mktfhe_cmux_step_batch(mktfhe_ctx *ctx, int party, int idx, const uint32_t *
  * atilde[g][ell] are the rotations of block `blk`'s key bits. */
 int mktfhe_block_step_batch(mktfhe_ctx *ctx, int party, int blk, const uint32_t *atilde, void *acc_rows,
                             size_t batch);
+/* One gadget product with the device functions FAST phase 2 is built from (KMS*, N = 2048):
+ *   out[g][c] = native(ifft( Sum_{j<l} fft(D_j(polys[g])) (.) keys[j][c] )),  c < ncomp <= 3, keys [l][ncomp][H] complex in the
+ *   reference slot order (the shape of a LEV product with levkey rows, bootstrapping.jl:483-499, of the u / v sums, :520-535, and
+ *   of w, :538-550).  Lets a test feed the oracle's intermediate polynomials into single products of phase 2. */
+int mktfhe_gadget_product_batch(mktfhe_ctx *ctx, int l, int logB, const uint64_t *polys, const double *keys, int ncomp,
+                                uint64_t *out, size_t batch);
 /* fftto! / ifftto! (fft.jl:57-63,74-81) and poly decompto! (gsw.jl:86-96) on `batch` polynomials.
  * bits = 32 / 64 selects the torus; spectra in the reference's slot order; STRICT arithmetic. */
 int mktfhe_fft_batch(mktfhe_ctx *ctx, int bits, const void *polys, double *spectra, size_t batch);

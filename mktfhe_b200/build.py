@@ -23,7 +23,7 @@ CUDA_LIB = os.path.join(LIBDIR, "libmktfhe_b200.so")
 
 HOST_SRCS = ["host_keygen.cpp"]
 CUDA_SRCS = ["capi.cu"]
-CUDA_DEPS = ["common.cuh", "fft_strict.cuh", "kernels_strict.cuh", "kernels_fast.cuh", "kernels_fast_w.cuh", "kernels_fast32.cuh", "keyswitch.cuh"]
+CUDA_DEPS = ["common.cuh", "fft_strict.cuh", "kernels_strict.cuh", "kernels_fast.cuh", "kernels_fast_w.cuh", "kernels_fast32.cuh", "keyswitch.cuh", "keygen.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -57,7 +57,10 @@ def build_host(force: bool = False) -> str:
     deps = srcs + [os.path.join(INCLUDE, h) for h in ("mktfhe_host.h", "mktfhe_params.h")]
     if force or _stale(HOST_LIB, deps):
         tmp = HOST_LIB + ".tmp"
-        _run(["g++", "-O2", "-march=x86-64-v3", "-std=gnu++17", "-fopenmp", "-fPIC", "-shared", "-Wall",
+        # -ffp-contract=off: the uploaded FFT form of the keys is the reference's Float64 transform (fft.jl:57-63,105-155), and
+        # Julia never contracts a*b + c into an fma; with contraction the spectra differ in the last bit from the oracle's and
+        # from the device key generation (csrc/keygen.cuh), which both follow the reference operation for operation.
+        _run(["g++", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-std=gnu++17", "-fopenmp", "-fPIC", "-shared", "-Wall",
               "-o", tmp] + srcs + ["-lquadmath"])
         os.replace(tmp, HOST_LIB)            # atomic: a repo snapshot never sees a half-written library
     return HOST_LIB

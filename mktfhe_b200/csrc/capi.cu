@@ -16,6 +16,7 @@
 #include "keyswitch.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_fast32.cuh"
+#include "keygen.cuh"
 
 namespace {
 
@@ -36,6 +37,7 @@ struct mktfhe_ctx {
     std::vector<cplx *> brk, rlk, pubb;
     std::vector<uint32_t *> ksk;
     cplx *crs = nullptr;
+    void *crs_coeff = nullptr;                       // device key generation: CRS in coefficient form, [l_uni][N] torus
     cplx **d_brk = nullptr, **d_rlk = nullptr, **d_pubb = nullptr;
     uint32_t **d_ksk = nullptr;
     bool finalized = false;
@@ -319,6 +321,190 @@ template <class T> int upload(mktfhe_ctx *ctx, T *&dst, const void *src, size_t 
     return 0;
 }
 
+// transform tables of the reference (fft.jl:26-44); needed by finalize and by the device key generation
+int ensure_tables(mktfhe_ctx *ctx) {
+    if (ctx->psi && ctx->psiinv && ctx->roots && ctx->rootsinv) return 0;
+    int rc;
+    std::vector<cplx> psi, psiinv, roots, rootsinv;
+    fft_tables_host(ctx->N, psi, psiinv, roots, rootsinv);
+    const size_t tb = sizeof(cplx) * ctx->H;
+    if ((rc = upload(ctx, ctx->psi, psi.data(), tb)) || (rc = upload(ctx, ctx->psiinv, psiinv.data(), tb)) ||
+        (rc = upload(ctx, ctx->roots, roots.data(), tb)) || (rc = upload(ctx, ctx->rootsinv, rootsinv.data(), tb)))
+        return rc;
+    return 0;
+}
+
+// ---- device key generation (csrc/keygen.cuh) -------------------------------------------------------------------
+kg::Key kg_key(uint64_t seed, const uint8_t *key32) {
+    kg::Key k;
+    if (key32) { memcpy(k.k, key32, 32); return k; }
+    uint64_t x = seed;                                  // splitmix64 expansion, as ChaCha20::Key::from_seed (host_keygen.cpp)
+    for (int i = 0; i < 4; i++) {
+        uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        k.k[2 * i] = (uint32_t)z; k.k[2 * i + 1] = (uint32_t)(z >> 32);
+    }
+    return k;
+}
+
+template <class T, int H> int kg_fft(mktfhe_ctx *ctx, const T *polys, cplx *out, size_t count) {
+    const int G = MK_THREADS / (H / 8);
+    const size_t smem = (size_t)G * padded_len(H) * sizeof(cplx);
+    k_fft_batch<T, H><<<(unsigned)((count + G - 1) / G), MK_THREADS, smem, ctx->stream>>>(polys, out, ctx->tables(), (int)count);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <class T, int NN> int kg_common(mktfhe_ctx *ctx, const kg::Key &key) {
+    const mktfhe_params &p = ctx->p;
+    const size_t count = (size_t)p.l_uni * NN;
+    dfree(ctx->crs_coeff); dfree(ctx->crs);
+    CK(cudaMalloc(&ctx->crs_coeff, count * sizeof(T)));
+    CK(cudaMalloc(&ctx->crs, mktfhe_crs_doubles(&p) * 8));
+    kg::k_kg_uniform<T><<<(unsigned)std::min<size_t>((count + 2047) / 2048, 1024), 256, 0, ctx->stream>>>(key, kg::stream_id(kg::S_CRS, 0, 0), (T *)ctx->crs_coeff, count);
+    CK(cudaGetLastError());
+    return kg_fft<T, NN / 2>(ctx, (const T *)ctx->crs_coeff, ctx->crs, p.l_uni);
+}
+
+template <class T, int NN> int kg_party(mktfhe_ctx *ctx, int party, const kg::Key &key) {
+    using Row = kg::RowDesc<T>;
+    const mktfhe_params &p = ctx->p;
+    constexpr int WT = sizeof(T) / 4, H = NN / 2;
+    const int n = p.n, bits = (int)sizeof(T) * 8;
+    const bool ccs = p.scheme == MKTFHE_CCS;
+    int rc;
+    int8_t *d_lwe = nullptr, *d_ring = nullptr, *d_gsw = nullptr, *d_r = nullptr;
+    T *tmp = nullptr;
+    Row *d_rows = nullptr;
+    auto cleanup = [&]() { dfree(d_lwe); dfree(d_ring); dfree(d_gsw); dfree(d_r); dfree(tmp); dfree(d_rows); };
+#define KG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, MKTFHE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    KG(cudaMalloc(&d_lwe, n)); KG(cudaMalloc(&d_ring, NN)); KG(cudaMalloc(&d_gsw, NN));
+    kg::k_kg_secrets<<<1, 256, (size_t)NN * 4, ctx->stream>>>(key, party, n, NN, ctx->block ? 1 : 0, p.d, p.ell, d_lwe, d_ring, d_gsw);
+    KG(cudaGetLastError());
+    std::vector<int8_t> h_lwe(n);
+    KG(cudaMemcpyAsync(h_lwe.data(), d_lwe, n, cudaMemcpyDeviceToHost, ctx->stream));
+    KG(cudaStreamSynchronize(ctx->stream));
+    const int8_t *brk_key = ctx->kms ? d_gsw : d_ring;          // RGSW key: gswkey for KMS*, ringkey for CGGI / LMSS
+    auto gvec = [&](int j, int logB) -> T { return (T)1 << (bits - (j + 1) * logB); };
+    KG(cudaFuncSetAttribute(kg::k_kg_rows<T, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kg::rows_smem<T, NN>()));
+    auto run_rows = [&](std::vector<Row> &rows) -> int {
+        dfree(d_rows);
+        KG(cudaMalloc(&d_rows, rows.size() * sizeof(Row)));
+        KG(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(Row), cudaMemcpyHostToDevice, ctx->stream));
+        kg::k_kg_rows<T, NN><<<(unsigned)rows.size(), 256, kg::rows_smem<T, NN>(), ctx->stream>>>(key, d_rows);
+        KG(cudaGetLastError());
+        KG(cudaStreamSynchronize(ctx->stream));                // `rows` (host) is read by the async copy
+        return 0;
+    };
+    // unienc rows of one stream (unienc.jl:36-75): polys [j][d, f.b, f.a] into dst
+    auto unienc_rows = [&](std::vector<Row> &rows, uint64_t stream, const int8_t *r_vec, const int8_t *msg_vec, T msg_scalar, T *dst) {
+        const int l = p.l_uni;
+        for (int j = 0; j < l; j++) {
+            Row d{};
+            d.stream = stream; d.e_off = (uint64_t)NN + (uint64_t)j * 2 * NN; d.a_given = (const T *)ctx->crs_coeff + (size_t)j * NN;
+            d.s = r_vec; d.sigma = p.beta; d.gen_a = 0; d.negate = 0;
+            d.out0 = dst + (size_t)(j * 3 + 0) * NN; d.out1 = nullptr;
+            if (msg_vec) { d.msg_mode = 3; d.msg_vec = msg_vec; d.msg = gvec(j, p.logB_uni); }
+            else { d.msg_mode = 1; d.msg = (T)(gvec(j, p.logB_uni) * msg_scalar); }
+            rows.push_back(d);
+        }
+        for (int j = 0; j < l; j++) {
+            Row f{};
+            f.stream = stream; f.a_off = (uint64_t)NN + (uint64_t)l * 2 * NN + (uint64_t)j * ((uint64_t)NN * WT + 2 * NN);
+            f.e_off = f.a_off + (uint64_t)NN * WT;
+            f.s = d_ring; f.sigma = p.beta; f.gen_a = 1; f.negate = 1;
+            f.msg_mode = 3; f.msg_vec = r_vec; f.msg = gvec(j, p.logB_uni);
+            f.out0 = dst + (size_t)(j * 3 + 1) * NN; f.out1 = dst + (size_t)(j * 3 + 2) * NN;
+            rows.push_back(f);
+        }
+    };
+
+    // ---- public key b (unienc.jl:77-90; keygen.jl:68,100,136)
+    if (ctx->mk) {
+        if (!ctx->crs_coeff) { cleanup(); return fail(ctx, MKTFHE_ERR_STATE, "CRS missing: call mktfhe_keygen_common first"); }
+        std::vector<Row> rows;
+        KG(cudaMalloc(&tmp, (size_t)p.l_uni * NN * sizeof(T)));
+        for (int j = 0; j < p.l_uni; j++) {
+            Row r{};
+            r.stream = kg::stream_id(kg::S_PUBB, party, 0); r.e_off = (uint64_t)j * 2 * NN;
+            r.a_given = (const T *)ctx->crs_coeff + (size_t)j * NN; r.s = d_ring; r.sigma = p.beta; r.gen_a = 0; r.negate = 1;
+            r.out0 = tmp + (size_t)j * NN;
+            rows.push_back(r);
+        }
+        if ((rc = run_rows(rows))) return rc;
+        dfree(ctx->pubb[party]);
+        KG(cudaMalloc(&ctx->pubb[party], mktfhe_pubb_doubles(&p) * 8));
+        if ((rc = kg_fft<T, H>(ctx, tmp, ctx->pubb[party], p.l_uni))) { cleanup(); return rc; }
+        KG(cudaStreamSynchronize(ctx->stream));
+        dfree(tmp);
+    }
+    // ---- rlk = UniEnc(gswkey) under the ring key (keygen.jl:103,139)
+    if (ctx->kms) {
+        std::vector<Row> rows;
+        KG(cudaMalloc(&d_r, NN));
+        kg::k_kg_ternary<<<1, 256, (size_t)NN * 4, ctx->stream>>>(key, kg::S_RLK, party, 0, NN, d_r);
+        KG(cudaGetLastError());
+        KG(cudaMalloc(&tmp, (size_t)3 * p.l_uni * NN * sizeof(T)));
+        unienc_rows(rows, kg::stream_id(kg::S_RLK, party, 0), d_r, d_gsw, (T)0, tmp);
+        if ((rc = run_rows(rows))) return rc;
+        dfree(ctx->rlk[party]);
+        KG(cudaMalloc(&ctx->rlk[party], mktfhe_rlk_doubles(&p) * 8));
+        if ((rc = kg_fft<T, H>(ctx, tmp, ctx->rlk[party], (size_t)3 * p.l_uni))) { cleanup(); return rc; }
+        KG(cudaStreamSynchronize(ctx->stream));
+        dfree(tmp); dfree(d_r);
+    }
+    // ---- brk (keygen.jl:12-14,39-41,71-73,106-108,143-145)
+    {
+        const size_t polys_per = ccs ? (size_t)3 * p.l_uni : (size_t)4 * p.l_gsw;
+        std::vector<Row> rows;
+        KG(cudaMalloc(&tmp, (size_t)n * polys_per * NN * sizeof(T)));
+        if (ccs) {
+            KG(cudaMalloc(&d_r, (size_t)n * NN));
+            kg::k_kg_ternary<<<n, 256, (size_t)NN * 4, ctx->stream>>>(key, kg::S_BRK, party, 0, NN, d_r);
+            KG(cudaGetLastError());
+            for (int i = 0; i < n; i++)
+                unienc_rows(rows, kg::stream_id(kg::S_BRK, party, (uint64_t)i), d_r + (size_t)i * NN, nullptr, (T)h_lwe[i], tmp + (size_t)i * polys_per * NN);
+        } else {
+            const int l = p.l_gsw;
+            for (int i = 0; i < n; i++)
+                for (int r = 0; r < 2 * l; r++) {
+                    const int basket = r / l, j = r % l;
+                    Row d{};
+                    d.stream = kg::stream_id(kg::S_BRK, party, (uint64_t)i);
+                    d.a_off = (uint64_t)r * ((uint64_t)NN * WT + 2 * NN); d.e_off = d.a_off + (uint64_t)NN * WT;
+                    d.s = brk_key; d.sigma = p.beta; d.gen_a = 1; d.negate = 1;
+                    d.msg_mode = basket == 0 ? 1 : 2; d.msg = (T)(gvec(j, p.logB_gsw) * (T)h_lwe[i]);
+                    d.out0 = tmp + ((size_t)i * polys_per + (size_t)r * 2 + 0) * NN; d.out1 = d.out0 + NN;
+                    rows.push_back(d);
+                }
+        }
+        if ((rc = run_rows(rows))) return rc;
+        dfree(ctx->brk[party]);
+        KG(cudaMalloc(&ctx->brk[party], mktfhe_brk_doubles(&p) * 8));
+        if ((rc = kg_fft<T, H>(ctx, tmp, ctx->brk[party], (size_t)n * polys_per))) { cleanup(); return rc; }
+        KG(cudaStreamSynchronize(ctx->stream));
+        dfree(tmp); dfree(d_r);
+    }
+    // ---- ksk (keygen.jl:16-24,43-52,75-79,110-114,147-151), stored with the 16-byte aligned row stride of uploaded keys
+    {
+        const int Dk = mktfhe_ksk_rows(&p), nrows = Dk * p.f, rowp = (n + 1 + 3) / 4 * 4;
+        const size_t words = (size_t)nrows * n + 4 * ((nrows + 1) / 2);
+        dfree(ctx->ksk[party]);
+        KG(cudaMalloc(&ctx->ksk[party], (size_t)NN * nrows * rowp * 4));
+        KG(cudaFuncSetAttribute(kg::k_kg_ksk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(words * 4)));
+        kg::k_kg_ksk<<<NN, 256, words * 4, ctx->stream>>>(key, party, n, NN, Dk, p.f, p.logD, ctx->block ? 1 : 0, p.alpha, d_lwe, d_ring,
+                                                       ctx->ksk[party], rowp);
+        KG(cudaGetLastError());
+        KG(cudaStreamSynchronize(ctx->stream));
+    }
+#undef KG
+    cleanup();
+    ctx->finalized = false;
+    return 0;
+}
+
 // 16 independent FMA chains per thread, 16 warps per SM: measured 36.9-37.0 TFLOP/s on B200 (tools/dfma_ilp.cu shows
 // the dependent-issue latency is ~9 cycles and that 2 warps per scheduler with 4 chains each already reach 93 %).
 __global__ void k_dfma_peak(double *out, int iters) {
@@ -552,6 +738,7 @@ void mktfhe_ctx_destroy(mktfhe_ctx *ctx) {
     for (auto &q : ctx->rlk) dfree(q);
     for (auto &q : ctx->pubb) dfree(q);
     for (auto &q : ctx->ksk) dfree(q);
+    dfree(ctx->crs_coeff);
     dfree(ctx->crs); dfree(ctx->psi); dfree(ctx->psiinv); dfree(ctx->roots); dfree(ctx->rootsinv); dfree(ctx->mono);
     dfree(ctx->d_brk); dfree(ctx->d_rlk); dfree(ctx->d_pubb); dfree(ctx->d_ksk);
     for (auto &s : ctx->events) for (auto &ev : s.e) cudaEventDestroy(ev);
@@ -609,6 +796,58 @@ int mktfhe_upload_common(mktfhe_ctx *ctx, const double *crs_fft) {
     return upload(ctx, ctx->crs, crs_fft, mktfhe_crs_doubles(&ctx->p) * 8);
 }
 
+int mktfhe_keygen_common(mktfhe_ctx *ctx, uint64_t seed, const uint8_t *key32) {
+    if (!ctx) return MKTFHE_ERR_ARG;
+    if (is_multi(ctx)) {
+        const int rc = mktfhe_keygen_common(ctx->children[0], seed, key32);
+        if (rc) ctx->err = ctx->children[0]->err;
+        return rc;
+    }
+    if (!ctx->mk) return 0;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_tables(ctx))) return rc;
+    const kg::Key key = kg_key(seed, key32);
+    rc = ctx->bits == 64 ? kg_common<uint64_t, 2048>(ctx, key) : kg_common<uint32_t, 1024>(ctx, key);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->finalized = false;
+    return 0;
+}
+
+int mktfhe_keygen_party(mktfhe_ctx *ctx, int party, uint64_t seed, const uint8_t *key32) {
+    if (!ctx) return MKTFHE_ERR_ARG;
+    if (is_multi(ctx)) {            // generated on the first device; mktfhe_finalize_keys replicates device to device
+        const int rc = mktfhe_keygen_party(ctx->children[0], party, seed, key32);
+        if (rc) ctx->err = ctx->children[0]->err;
+        return rc;
+    }
+    if (party < 0 || party >= ctx->nparties) return fail(ctx, MKTFHE_ERR_ARG, "bad party index");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_tables(ctx))) return rc;
+    const kg::Key key = kg_key(seed, key32);
+    return ctx->bits == 64 ? kg_party<uint64_t, 2048>(ctx, party, key) : kg_party<uint32_t, 1024>(ctx, party, key);
+}
+
+int mktfhe_download_party_key(mktfhe_ctx *ctx, int party, double *brk, double *rlk, double *pubb, uint32_t *ksk, double *crs_fft) {
+    if (!ctx) return MKTFHE_ERR_ARG;
+    if (is_multi(ctx)) return mktfhe_download_party_key(ctx->children[0], party, brk, rlk, pubb, ksk, crs_fft);
+    if (party < 0 || party >= ctx->nparties) return fail(ctx, MKTFHE_ERR_ARG, "bad party index");
+    CK(cudaSetDevice(ctx->device));
+    const mktfhe_params &p = ctx->p;
+    if (brk) { if (!ctx->brk[party]) return fail(ctx, MKTFHE_ERR_STATE, "no brk"); CK(cudaMemcpy(brk, ctx->brk[party], mktfhe_brk_doubles(&p) * 8, cudaMemcpyDeviceToHost)); }
+    if (rlk) { if (!ctx->rlk[party]) return fail(ctx, MKTFHE_ERR_STATE, "no rlk"); CK(cudaMemcpy(rlk, ctx->rlk[party], mktfhe_rlk_doubles(&p) * 8, cudaMemcpyDeviceToHost)); }
+    if (pubb) { if (!ctx->pubb[party]) return fail(ctx, MKTFHE_ERR_STATE, "no pubb"); CK(cudaMemcpy(pubb, ctx->pubb[party], mktfhe_pubb_doubles(&p) * 8, cudaMemcpyDeviceToHost)); }
+    if (crs_fft) { if (!ctx->crs) return fail(ctx, MKTFHE_ERR_STATE, "no crs"); CK(cudaMemcpy(crs_fft, ctx->crs, mktfhe_crs_doubles(&p) * 8, cudaMemcpyDeviceToHost)); }
+    if (ksk) {
+        if (!ctx->ksk[party]) return fail(ctx, MKTFHE_ERR_STATE, "no ksk");
+        const size_t rows = (size_t)ctx->N * mktfhe_ksk_rows(&p) * p.f, row = (size_t)p.n + 1, rowp = (row + 3) / 4 * 4;
+        CK(cudaMemcpy2D(ksk, row * 4, ctx->ksk[party], rowp * 4, row * 4, rows, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
 int mktfhe_finalize_keys(mktfhe_ctx *ctx) {
     if (!ctx) return MKTFHE_ERR_ARG;
     if (is_multi(ctx)) {
@@ -628,12 +867,7 @@ int mktfhe_finalize_keys(mktfhe_ctx *ctx) {
         if (!ctx->brk[i] || !ctx->ksk[i]) return fail(ctx, MKTFHE_ERR_STATE, "party key missing: " + std::to_string(i));
     if (ctx->mk && !ctx->crs) return fail(ctx, MKTFHE_ERR_STATE, "common reference string missing");
     int rc;
-    std::vector<cplx> psi, psiinv, roots, rootsinv;
-    fft_tables_host(ctx->N, psi, psiinv, roots, rootsinv);
-    const size_t tb = sizeof(cplx) * ctx->H;
-    if ((rc = upload(ctx, ctx->psi, psi.data(), tb)) || (rc = upload(ctx, ctx->psiinv, psiinv.data(), tb)) ||
-        (rc = upload(ctx, ctx->roots, roots.data(), tb)) || (rc = upload(ctx, ctx->rootsinv, rootsinv.data(), tb)))
-        return rc;
+    if ((rc = ensure_tables(ctx))) return rc;
     if ((rc = upload(ctx, ctx->d_brk, ctx->brk.data(), sizeof(void *) * ctx->nparties))) return rc;
     if ((rc = upload(ctx, ctx->d_ksk, ctx->ksk.data(), sizeof(void *) * ctx->nparties))) return rc;
     if ((rc = upload(ctx, ctx->d_rlk, ctx->rlk.data(), sizeof(void *) * ctx->nparties))) return rc;
@@ -1029,6 +1263,35 @@ int mktfhe_decomp_batch(mktfhe_ctx *ctx, int bits, int l, int logB, const void *
     if (!polys || !digits || (bits != 32 && bits != 64) || l < 1 || l > MK_MAXL * 2 || logB < 1 || l * logB > bits)
         return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
     return bits == 64 ? decomp_hook<uint64_t>(ctx, l, logB, polys, digits, batch) : decomp_hook<uint32_t>(ctx, l, logB, polys, digits, batch);
+}
+
+int mktfhe_gadget_product_batch(mktfhe_ctx *ctx, int l, int logB, const uint64_t *polys, const double *keys, int ncomp, uint64_t *out, size_t batch) {
+    int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_gadget_product_batch");
+    if ((rc = check_ready(ctx))) return rc;
+    if (!ctx->kms || !fast_supported(ctx->p)) return fail(ctx, MKTFHE_ERR_PARAMS, "the gadget product hook exists for the FAST KMS path (N = 2048) only");
+    if (!polys || !keys || !out || l < 1 || l > MK_MAXL || logB < 1 || l * logB > 64 || ncomp < 1 || ncomp > 3) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
+    if (batch == 0) return 0;
+    uint64_t *d_in = nullptr, *d_out = nullptr; cplx *d_keys = nullptr;
+    const size_t nk = (size_t)l * ncomp * ctx->H;
+    auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(d_keys); };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_in, batch * ctx->N * 8)) != cudaSuccess || (e = cudaMalloc(&d_out, batch * ncomp * ctx->N * 8)) != cudaSuccess ||
+        (e = cudaMalloc(&d_keys, nk * sizeof(cplx))) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_in, polys, batch * ctx->N * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_keys, keys, nk * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, MKTFHE_ERR_CUDA, cudaGetErrorString(e));
+    }
+    rc = fast_gadget_product(ctx->fast, d_in, d_keys, d_out, l, logB, ncomp, batch, ctx->stream, &ctx->launches, ctx->err);
+    if (!rc) {
+        if ((e = cudaMemcpyAsync(out, d_out, batch * ncomp * ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+            rc = fail(ctx, MKTFHE_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cleanup();
+    return rc;
 }
 
 int mktfhe_measure_dfma_peak(mktfhe_ctx *ctx, double *tflops_out) {

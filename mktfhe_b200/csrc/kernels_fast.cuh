@@ -1486,6 +1486,54 @@ __global__ void __launch_bounds__(CTA, 1) k_phase2(const P2Args a) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tm_base_s));
 }
 
+// ---- gadget product hook: the building block of FAST phase 2 on caller-supplied inputs --------------------------------------
+// out[c] = native(ifft( Sum_j fft(D_j(poly)) (.) key[j][c] ))  for c < ncomp, with the SAME device functions k_phase2 is made of
+// (p2_digits, fft_fwd2, multiply-accumulate, fft_inv2, d2torus).  Phase 2 chains such products and re-decomposes their
+// outputs, so whole-phase coefficients cannot be compared between two roundings; this hook lets a test feed the ORACLE's
+// intermediate polynomial into one product and compare the result within a per-product tolerance
+// (bootstrapping.jl:483-499 LEV product, :520-535 u / v, :538-550 w).  keys: [l][ncomp][H] in the reference slot order.
+struct GpArgs {
+    const uint64_t *polys;      // [B][N]
+    const cplx *keys;           // [l][ncomp][H]
+    uint64_t *out;              // [B][ncomp][N]
+    Tables tb;
+    int l, logB, ncomp;
+    size_t units;
+};
+__global__ void __launch_bounds__(CTA, 1) k_gadget_product(const GpArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, unit_l = tid / UT, t = tid % UT;
+    cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + U * SMEM_UNIT_TM), *tw8 = tw2 + 128, *tw9e = tw8 + 128;
+    for (int i = tid; i < 256; i += CTA) { if (i < 128) { tw2[i] = a.tb.t2[i]; tw8[i] = a.tb.t8[i]; } tw9e[i] = a.tb.t9[i]; }
+    cplx *xa = reinterpret_cast<cplx *>(smem_raw + unit_l * SMEM_UNIT_TM), *xc = xa + XB_LEN;
+    __syncthreads();
+    const size_t unit = (size_t)blockIdx.x * U + unit_l;
+    if (unit >= a.units) return;
+    uint32_t lo[32], hi[32];
+    const uint64_t *src = a.polys + unit * N;
+#pragma unroll
+    for (int m = 0; m < 32; m++) { const uint64_t v = src[t + 64 * (m & 15) + (m >> 4) * H]; lo[m] = (uint32_t)v; hi[m] = (uint32_t)(v >> 32); }
+    for (int c = 0; c < a.ncomp; c++) {
+        cplx acc[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) acc[e] = make_double2(0.0, 0.0);
+        for (int j = 0; j < a.l; j++) {
+            cplx x[16];
+            p2_digits(lo, hi, j, a.l, a.logB, x);
+            fft_fwd2(x, xa, xc, tw2, tw8, tw9e, t, unit_l, []() {}, []() {});
+            const cplx *k = a.keys + ((size_t)j * a.ncomp + c) * H + 16 * t;          // slot 16t + e
+#pragma unroll
+            for (int e = 0; e < 16; e++) acc[e] = cmac_f(acc[e], x[e], k[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; e++) acc[e] = make_double2(acc[e].x * (1.0 / H), acc[e].y * (1.0 / H));
+        fft_inv2(acc, xa, xc, tw2, tw8, tw9e, t, unit_l);
+        uint64_t *dst = a.out + (unit * a.ncomp + c) * N;
+#pragma unroll
+        for (int m = 0; m < 16; m++) { dst[t + 64 * m] = d2torus(acc[m].x); dst[t + 64 * m + H] = d2torus(-acc[m].y); }
+    }
+}
+
 // reference slot order [poly][16t + e] -> thread order [poly][e][t], scaled (1/H for the phase-2 keys)
 __global__ void k_permute_scale(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys, double scale) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1726,6 +1774,20 @@ static inline int fast_phase2(FastKeys &f, const mktfhe_params &p, const uint32_
     a.k = p.k; a.l_lev = p.l_lev; a.logB_lev = p.logB_lev; a.l_uni = p.l_uni; a.logB_uni = p.logB_uni;
     a.R = 1 + (p.k - 1) * p.l_lev; a.lwe_words = (int)mktfhe_lwe_words(&p); a.gates = gates;
     k_phase2<<<(unsigned)((gates + U - 1) / U), CTA, SMEM_BYTES_TM, stream>>>(a);
+    if (launches) (*launches)++;
+    FCK(cudaGetLastError());
+    return 0;
+}
+
+static inline int fast_gadget_product(FastKeys &f, const uint64_t *polys, const cplx *keys, uint64_t *out, int l, int logB, int ncomp,
+                                      size_t batch, cudaStream_t stream, int *launches, std::string &err) {
+    using namespace fast;
+    if (!f.built) { err = "FAST keys not built"; return -3; }
+    GpArgs a{};
+    a.polys = polys; a.keys = keys; a.out = out; a.tb = Tables{f.t2, f.t8, f.t9, f.emono, f.t2w};
+    a.l = l; a.logB = logB; a.ncomp = ncomp; a.units = batch;
+    FCK(cudaFuncSetAttribute(k_gadget_product, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TM));
+    k_gadget_product<<<(unsigned)((batch + U - 1) / U), CTA, SMEM_BYTES_TM, stream>>>(a);
     if (launches) (*launches)++;
     FCK(cudaGetLastError());
     return 0;

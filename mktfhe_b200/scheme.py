@@ -88,6 +88,37 @@ class Scheme:
     def finalize(self):
         self._ck(_lib.lib().mktfhe_finalize_keys(self._h), "mktfhe_finalize_keys")
 
+    # -- key generation on the device (include/mktfhe_b200.h, "key generation on the device") --------------
+    @staticmethod
+    def _seed_args(seed):
+        from . import _host
+        if _host.is_key(seed):
+            buf = ctypes.create_string_buffer(bytes(seed), 32)
+            return 0, ctypes.cast(buf, ctypes.c_void_p), buf
+        return int(seed), None, None
+
+    def keygen_common(self, seed):
+        """CRS + its FFT form generated on the device (scheme.jl:409-410).  seed: int (reproducible) or 32-byte key."""
+        s, k, keep = self._seed_args(seed)
+        self._ck(_lib.lib().mktfhe_keygen_common(self._h, s, k), "mktfhe_keygen_common")
+
+    def keygen_party(self, party: int, seed):
+        """Evaluation keys of `party` generated on the device from the same streams as the host library (keygen.jl:3-155)."""
+        s, k, keep = self._seed_args(seed)
+        self._ck(_lib.lib().mktfhe_keygen_party(self._h, party, s, k), "mktfhe_keygen_party")
+
+    def download_party_key(self, party: int) -> dict:
+        """Parity hook: a party's keys as they sit in device memory, in the flat upload layouts."""
+        p = self.params
+        out = {"brk": np.empty((p.n, p.brk_polys, p.H, 2), dtype=np.float64),
+               "ksk": np.empty((p.N, p.ksk_rows, p.f, p.n + 1), dtype=np.uint32),
+               "rlk": np.empty((p.l_uni, 3, p.H, 2), dtype=np.float64) if p.scheme in (3, 4) else None,
+               "pubb": np.empty((p.l_uni, p.H, 2), dtype=np.float64) if p.is_mk else None,
+               "crs_fft": np.empty((p.l_uni, p.H, 2), dtype=np.float64) if p.is_mk else None}
+        self._ck(_lib.lib().mktfhe_download_party_key(self._h, party, _ptr(out["brk"]), _ptr(out["rlk"]), _ptr(out["pubb"]),
+                                                      _ptr(out["ksk"]), _ptr(out["crs_fft"])), "mktfhe_download_party_key")
+        return out
+
     def set_mode(self, mode: int):
         self._ck(_lib.lib().mktfhe_set_mode(self._h, mode), "mktfhe_set_mode")
 
@@ -211,6 +242,16 @@ class Scheme:
         self._ck(_lib.lib().mktfhe_block_step_batch(self._h, party, blk, _ptr(at), _ptr(rows), rows.shape[0]), "block_step")
         return rows
 
+    def gadget_product(self, polys, keys, l, logB):
+        """out[g][c] = native(ifft(Sum_j fft(D_j(polys[g])) * keys[j][c])): one product of FAST phase 2 (KMS*)."""
+        polys = np.ascontiguousarray(polys, dtype=np.uint64)
+        keys = np.ascontiguousarray(keys, dtype=np.float64)            # [l][ncomp][H][2]
+        assert keys.shape[0] == l and keys.shape[2:] == (self.params.H, 2)
+        out = np.empty((polys.shape[0], keys.shape[1], self.params.N), dtype=np.uint64)
+        self._ck(_lib.lib().mktfhe_gadget_product_batch(self._h, l, logB, _ptr(polys), _ptr(keys), keys.shape[1], _ptr(out),
+                                                        polys.shape[0]), "gadget_product")
+        return out
+
     def fft(self, polys):
         polys = np.ascontiguousarray(polys)
         bits = polys.dtype.itemsize * 8
@@ -242,6 +283,21 @@ class Scheme:
         v = ctypes.c_double()
         self._ck(_lib.lib().mktfhe_measure_dfma_peak(self._h, ctypes.byref(v)), "dfma_peak")
         return v.value
+
+
+def setup_generated(params: Params, seed, device: int = 0, mode: int | None = None, devices=None):
+    """Like `setup`, with every evaluation key generated ON THE DEVICE (no host key generation, no upload): returns
+    (Scheme, KeySet) where the KeySet holds the secret keys only (same seed, host) for encrypting and decrypting.
+    seed: int.  For a given seed the device keys are byte-identical to KeySet(params, seed)'s."""
+    s = Scheme(params, device, devices)
+    if params.is_mk:
+        s.keygen_common(seed)
+    for i in range(params.k if params.is_mk else 1):
+        s.keygen_party(i, seed)
+    s.finalize()
+    if mode is not None:
+        s.set_mode(mode)
+    return s, KeySet(params, seed=seed, secret_only=True)
 
 
 def setup(keys: KeySet, device: int = 0, mode: int | None = None, devices=None) -> Scheme:
