@@ -90,11 +90,19 @@ function flatten_ksk(ksk, n, f)     # Array{LEV}(Dk, N) or (Dk, N, 1): [c][digit
     buf
 end
 
-"""One-time upload: hooks after `setup` (src/tfhe/scheme.jl:151,190,244,292,343)."""
-function upload(scheme, params; device::Integer = 0)
+"""One-time upload: hooks after `setup` (src/tfhe/scheme.jl:151,190,244,292,343).
+`devices = 0:7` puts ONE front context over several GPUs (mktfhe_ctx_create_multi): the keys go host -> first GPU once, are
+replicated GPU -> GPU at finalize, and every NAND(cs1, cs2, gpu) batch is sharded in contiguous slices inside the library."""
+function upload(scheme, params; device::Integer = 0, devices = nothing)
     cp = Ref(cparams(params))
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:mktfhe_ctx_create, LIB), Cint, (Ref{CParams}, Cint, Ref{Ptr{Cvoid}}), cp, device, h), C_NULL)
+    if devices === nothing
+        check(ccall((:mktfhe_ctx_create, LIB), Cint, (Ref{CParams}, Cint, Ref{Ptr{Cvoid}}), cp, device, h), C_NULL)
+    else
+        devs = Cint.(collect(devices))
+        GC.@preserve devs check(ccall((:mktfhe_ctx_create_multi, LIB), Cint, (Ref{CParams}, Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}),
+                                      cp, length(devs), devs, h), C_NULL)
+    end
     n = cp[].n
     btks = scheme.btk isa AbstractVector ? scheme.btk : [scheme.btk]
     for (i, btk) in enumerate(btks)

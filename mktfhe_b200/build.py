@@ -80,7 +80,9 @@ def build_cuda(force: bool = False) -> str:
         [os.path.join(INCLUDE, h) for h in ("mktfhe_b200.h", "mktfhe_params.h")]
     if force or _stale(CUDA_LIB, deps):
         tmp = CUDA_LIB + ".tmp"
-        _run([nvcc_path()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", tmp] + srcs + ["-lquadmath"],
+        # MKTFHE_DEBUG_SPIN=1: every mbarrier wait is bounded and traps instead of hanging (csrc/kernels_fast.cuh)
+        dbg = ["-DMKTFHE_DEBUG_SPIN"] if os.environ.get("MKTFHE_DEBUG_SPIN") == "1" else []
+        _run([nvcc_path()] + NVCC_FLAGS + dbg + ["-I", INCLUDE, "-o", tmp] + srcs + ["-lquadmath"],
              log=os.path.join(LIBDIR, "nvcc_build.log"))
         os.replace(tmp, CUDA_LIB)
     return CUDA_LIB

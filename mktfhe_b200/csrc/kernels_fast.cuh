@@ -909,7 +909,28 @@ __device__ __forceinline__ bool mb_try_hint(uint64_t *bar, uint32_t parity, uint
                  "selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity), "r"(ns) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mb_wait(uint64_t *bar, uint32_t parity) {
+// consumer-side wait: tight try_wait loop (try_wait + one predicated branch on the success path; measured faster than the
+// suspended form when the data is usually there: key switch 9.8 vs 10.3 ms).
+// Built with -DMKTFHE_DEBUG_SPIN (MKTFHE_DEBUG_SPIN=1 python -m mktfhe_b200.build --force) every wait is BOUNDED: 2^28 failed polls
+// (> 1 s) trap instead of hanging the device until the watchdog -- the build to use while changing a ring or token protocol.
+// The counter and the trap cost 3-6 % in the kernels that poll often (key switch 9.8 -> 10.1 ms, KMS8 block phase 1 672 -> 715 ms:
+// the trap makes the loop a divergence point), so production builds spin without them.
+__device__ __forceinline__ void mbs_spin(uint32_t bar, uint32_t parity) {
+#ifdef MKTFHE_DEBUG_SPIN
+    asm volatile("{\n.reg .pred p, q;\n.reg .u32 cnt;\nmov.u32 cnt, 0;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "add.u32 cnt, cnt, 1;\nsetp.gt.u32 q, cnt, 268435456;\n@q trap;\n"
+                 "bra WAIT_%=;\nDONE_%=:\n}" :: "r"(bar), "r"(parity) : "memory");
+#else
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(bar), "r"(parity) : "memory");
+#endif
+}
+__device__ __forceinline__ void mb_wait(uint64_t *bar, uint32_t parity) { mbs_spin((uint32_t)__cvta_generic_to_shared(bar), parity); }
+// producer-side wait: suspended in hardware between polls (a spinning producer took a quarter of its scheduler's issue slots)
+__device__ __forceinline__ void mb_wait_suspend(uint64_t *bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mb_try_hint(bar, parity, 20000u))
         if (++spins > (1u << 22)) __trap();
@@ -966,7 +987,7 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
         if (tid == CTA) {
             for (uint32_t n = 0; n < ntiles; n++) {
                 const int slot = n % RING;
-                if (n >= RING) mb_wait(&empty[slot], ((n / RING) - 1) & 1);
+                if (n >= RING) mb_wait_suspend(&empty[slot], ((n / RING) - 1) & 1);
                 // tile n = ((((step * 2l + dg) * HALVES + half) * ELL + b) * 2 + comp)
                 const uint32_t comp = n & 1, b = (n >> 1) % ELL, hf = ((n >> 1) / ELL) % HALVES;
                 const uint32_t dg = ((n >> 1) / ELL / HALVES) % (2 * l), step = (n >> 1) / ELL / HALVES / (2 * l);
@@ -1654,6 +1675,7 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
         FCK(cudaMemcpyToSymbol(fastw::c_tw1w, tw1w.data(), sizeof(cplx) * 32));
         FCK(cudaMemcpyToSymbol(fastw::c_e32, e32.data(), sizeof(cplx) * 32));
         FCK(cudaFuncSetAttribute(fastw::k_phase1_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fastw::SMEM_BYTES_W));
+
     }
     FCK(cudaMalloc(&f.t2, sizeof(cplx) * 128));
     FCK(cudaMalloc(&f.t8, sizeof(cplx) * 128));

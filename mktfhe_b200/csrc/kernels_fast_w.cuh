@@ -76,131 +76,47 @@ __device__ __forceinline__ void pass1_inv(cplx (&x)[32]) {
         }
     }
 }
-// ---- butterflies with a per-thread (register) twiddle, written for the operand-reuse cache --------------------------------
-// A DFMA with three distinct register sources takes 3 issue cycles on B200 instead of 2 (tools/fp64_issue.cu: the register file
-// delivers two fresh 64-bit sources per cycle pair); a source repeated in the same operand slot of consecutive instructions comes
-// from the reuse cache for free.  So a group of G butterflies that share a twiddle runs as three sweeps: all first products
-// (first source w.x), all second products (first source w.y), all "2a - lo" completions (two sources).
-template <int G>
-__device__ __forceinline__ void bf_group(cplx (&x)[32], const int (&ia)[G], const int (&ib)[G], const bool (&mi)[G], const cplx w) {
-    double t1[G], t2[G];
-#pragma unroll
-    for (int i = 0; i < G; i++) {
-        const cplx a = x[ia[i]], b = x[ib[i]];
-        if (!mi[i]) { t1[i] = fma(w.x, b.x, a.x); t2[i] = fma(w.x, b.y, a.y); }
-        else { t1[i] = fma(w.x, b.y, a.x); t2[i] = fma(-w.x, b.x, a.y); }
-    }
-#pragma unroll
-    for (int i = 0; i < G; i++) {
-        const cplx b = x[ib[i]];
-        if (!mi[i]) { t1[i] = fma(-w.y, b.y, t1[i]); t2[i] = fma(w.y, b.x, t2[i]); }
-        else { t1[i] = fma(w.y, b.x, t1[i]); t2[i] = fma(w.y, b.y, t2[i]); }
-    }
-#pragma unroll
-    for (int i = 0; i < G; i++) {
-        const cplx a = x[ia[i]];
-        x[ib[i]] = make_double2(fma(2.0, a.x, -t1[i]), fma(2.0, a.y, -t2[i]));
-        x[ia[i]] = make_double2(t1[i], t2[i]);
-    }
-}
-// inverse (unscaled): (A, B) -> (A + B, (A - B) * conj(w)); mi: twiddle -i*w
-template <int G>
-__device__ __forceinline__ void bi_group(cplx (&x)[32], const int (&ia)[G], const int (&ib)[G], const bool (&mi)[G], const cplx w) {
-    double p1[G], p2[G];
-#pragma unroll
-    for (int i = 0; i < G; i++) {
-        const cplx a = x[ia[i]], b = x[ib[i]];
-        x[ia[i]] = make_double2(a.x + b.x, a.y + b.y);
-        x[ib[i]] = make_double2(a.x - b.x, a.y - b.y);          // d
-    }
-#pragma unroll
-    for (int i = 0; i < G; i++) {
-        const cplx d = x[ib[i]];
-        // plain: b = (wx*dx + wy*dy, wx*dy - wy*dx);  mi: b = (-(wx*dy - wy*dx), wx*dx + wy*dy)
-        p1[i] = w.x * d.x; p2[i] = w.x * d.y;
-    }
-#pragma unroll
-    for (int i = 0; i < G; i++) {
-        const cplx d = x[ib[i]];
-        const double re = fma(w.y, d.y, p1[i]), im = fma(-w.y, d.x, p2[i]);
-        x[ib[i]] = mi[i] ? make_double2(-im, re) : make_double2(re, im);
-    }
-}
-
 // stages 6..10 on the thread's 32 contiguous slots; tw = shared table [16][32] + lane:
 //   row 0: TW[32 + t]; row 1: TW[64 + 2t]; rows 2+g: TW[128 + 4t + 2g]; rows 4+g: TW[256 + 8t + 2g]; rows 8+g: TW[512 + 16t + 2g]
-// Stage s (6..10) pairs e and e + half (half = 16 >> (s - 6)); the butterflies whose node shares an even sibling use one table row.
-template <bool INV, int S, int ROW, int PART, int G>
-__device__ __forceinline__ void pass2_row(cplx (&x)[32], const cplx w) {
-    // stage S, table row ROW (g = ROW - 2^(S-7) for S >= 7): elements e with (e >> (12 - S)) == g, i.e. sub = e >> (11 - S) in {2g, 2g+1}
-    constexpr int half = 16 >> (S - 6);
-    constexpr int per_row = (S == 6) ? 16 : (32 >> (S - 6));        // butterflies served by this row
-    constexpr int g = (S == 6) ? 0 : ROW - (1 << (S - 7));
-    int ia[G], ib[G]; bool mi[G];
-    int n = 0, seen = 0;
-#pragma unroll
-    for (int e = 0; e < 32; e++) {
-        if (e & half) continue;
-        const int sub = (S == 6) ? 0 : (e >> (11 - S));
-        if (S != 6 && (sub >> 1) != g) continue;
-        if (seen >= PART * G && seen < (PART + 1) * G) { ia[n] = e; ib[n] = e + half; mi[n] = (S != 6) && (sub & 1); n++; }
-        seen++;
-    }
-    static_assert(G <= per_row && per_row % G == 0, "group size");
-    if (INV) bi_group<G>(x, ia, ib, mi, w); else bf_group<G>(x, ia, ib, mi, w);
-}
+// (A variant that swept the butterflies of one twiddle in source order -- all products with w.x, all with w.y, all completions --
+// to feed the operand-reuse cache was measured: ptxas reschedules to the same mix, 21 % of the FP64 instructions keep three fresh
+// register sources, run time unchanged within noise.)
 __device__ __forceinline__ void pass2_fwd(cplx (&x)[32], const cplx *__restrict__ tw) {
-    { const cplx w = tw[0]; pass2_row<false, 6, 0, 0, 8>(x, w); pass2_row<false, 6, 0, 1, 8>(x, w); }
-    { const cplx w = tw[32]; pass2_row<false, 7, 1, 0, 8>(x, w); pass2_row<false, 7, 1, 1, 8>(x, w); }
-    pass2_row<false, 8, 2, 0, 8>(x, tw[2 * 32]); pass2_row<false, 8, 3, 0, 8>(x, tw[3 * 32]);
+    {
+        const cplx w = tw[0];
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const cplx w = tw[(4 + r) * 32];
-        if (r == 0) pass2_row<false, 9, 4, 0, 4>(x, w);
-        if (r == 1) pass2_row<false, 9, 5, 0, 4>(x, w);
-        if (r == 2) pass2_row<false, 9, 6, 0, 4>(x, w);
-        if (r == 3) pass2_row<false, 9, 7, 0, 4>(x, w);
+        for (int e = 0; e < 16; e++) bf(x[e], x[e + 16], w);
     }
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const cplx w = tw[(8 + r) * 32];
-        if (r == 0) pass2_row<false, 10, 8, 0, 2>(x, w);
-        if (r == 1) pass2_row<false, 10, 9, 0, 2>(x, w);
-        if (r == 2) pass2_row<false, 10, 10, 0, 2>(x, w);
-        if (r == 3) pass2_row<false, 10, 11, 0, 2>(x, w);
-        if (r == 4) pass2_row<false, 10, 12, 0, 2>(x, w);
-        if (r == 5) pass2_row<false, 10, 13, 0, 2>(x, w);
-        if (r == 6) pass2_row<false, 10, 14, 0, 2>(x, w);
-        if (r == 7) pass2_row<false, 10, 15, 0, 2>(x, w);
+    for (int s = 6; s < 10; s++) {
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            const int half = 16 >> (s - 5);
+            if (e & half) continue;
+            const int sub = e >> (10 - s);
+            const cplx w = tw[((1 << (s - 6)) + (sub >> 1)) * 32];
+            if (sub & 1) bf_mi(x[e], x[e + half], w); else bf(x[e], x[e + half], w);
+        }
     }
 }
 __device__ __forceinline__ void pass2_inv(cplx (&x)[32], const cplx *__restrict__ tw) {
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const cplx w = tw[(8 + r) * 32];
-        if (r == 0) pass2_row<true, 10, 8, 0, 2>(x, w);
-        if (r == 1) pass2_row<true, 10, 9, 0, 2>(x, w);
-        if (r == 2) pass2_row<true, 10, 10, 0, 2>(x, w);
-        if (r == 3) pass2_row<true, 10, 11, 0, 2>(x, w);
-        if (r == 4) pass2_row<true, 10, 12, 0, 2>(x, w);
-        if (r == 5) pass2_row<true, 10, 13, 0, 2>(x, w);
-        if (r == 6) pass2_row<true, 10, 14, 0, 2>(x, w);
-        if (r == 7) pass2_row<true, 10, 15, 0, 2>(x, w);
-    }
+    for (int s = 9; s >= 6; s--) {
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const cplx w = tw[(4 + r) * 32];
-        if (r == 0) pass2_row<true, 9, 4, 0, 4>(x, w);
-        if (r == 1) pass2_row<true, 9, 5, 0, 4>(x, w);
-        if (r == 2) pass2_row<true, 9, 6, 0, 4>(x, w);
-        if (r == 3) pass2_row<true, 9, 7, 0, 4>(x, w);
+        for (int e = 0; e < 32; e++) {
+            const int half = 16 >> (s - 5);
+            if (e & half) continue;
+            const int sub = e >> (10 - s);
+            const cplx w = tw[((1 << (s - 6)) + (sub >> 1)) * 32];
+            if (sub & 1) bi_mi(x[e], x[e + half], w); else bi(x[e], x[e + half], w);
+        }
     }
-    pass2_row<true, 8, 2, 0, 8>(x, tw[2 * 32]); pass2_row<true, 8, 3, 0, 8>(x, tw[3 * 32]);
-    { const cplx w = tw[32]; pass2_row<true, 7, 1, 0, 8>(x, w); pass2_row<true, 7, 1, 1, 8>(x, w); }
-    { const cplx w = tw[0]; pass2_row<true, 6, 0, 0, 8>(x, w); pass2_row<true, 6, 0, 1, 8>(x, w); }
+    {
+        const cplx w = tw[0];
+#pragma unroll
+        for (int e = 0; e < 16; e++) bi(x[e], x[e + 16], w);
+    }
 }
-// xb: this warp's exchange buffer; element n lives at n + (n >> 5): writes (lane-consecutive) and reads (stride 33) are
-// conflict-free for 16-byte accesses
 __device__ __forceinline__ void fft_fwd(cplx (&x)[32], cplx *xb, const cplx *tw, int t) {
     pass1_fwd(x);
     __syncwarp();                                       // earlier readers of xb are done
@@ -227,11 +143,12 @@ __device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0,
 __device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void mb_wait_sleep(uint64_t *bar, uint32_t parity) { fast::mb_wait(bar, parity); }
+__device__ __forceinline__ void mb_wait_sleep(uint64_t *bar, uint32_t parity) { fast::mb_wait_suspend(bar, parity); }
 // the same on 32-bit shared-window addresses computed once per kernel: the generic -> shared conversion at every call site cost
 // an S2UR + ULEA with a scoreboard wait each (1.5 % of the consumer warps' time in the v3 profile)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbs_wait(uint32_t bar, uint32_t parity) {
+template <int SUSPEND> __device__ __forceinline__ void mbs_wait(uint32_t bar, uint32_t parity) {
+    if (!SUSPEND) { fast::mbs_spin(bar, parity); return; }
     uint32_t spins = 0, ok = 0;
     do {
         asm volatile("{\n.reg .pred p;\n"
@@ -242,10 +159,10 @@ __device__ __forceinline__ void mbs_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbs_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
 // token = mbarrier with one arrival per phase; the waiter keeps the phase parity
-struct Token {
+template <int SUSPEND> struct Token {
     uint32_t bar;          // shared-window address
     uint32_t par;
-    __device__ __forceinline__ void wait() { mbs_wait(bar, par); par ^= 1; }
+    __device__ __forceinline__ void wait() { mbs_wait<SUSPEND>(bar, par); par ^= 1; }
 };
 __device__ __forceinline__ void token_pass(uint32_t bar, int t) {     // all lanes' TMEM stores are complete (tcgen05.wait::st)
     __syncwarp();
@@ -261,7 +178,10 @@ __device__ __forceinline__ cplx unpack_c(const uint32_t (&v)[16], int i) {
     return make_double2(__hiloint2double((int)v[4 * i + 1], (int)v[4 * i]), __hiloint2double((int)v[4 * i + 3], (int)v[4 * i + 2]));
 }
 
+// Producer waits are suspended in hardware (measured: 209 ms against 215 ms with a spinning producer at KMS2party, 4096 gates);
+// consumer waits spin (suspended consumer waits measured the same within noise).
 __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
+    constexpr int SUSPEND = 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, t = tid & 31;
     cplx *xb_all = reinterpret_cast<cplx *>(smem_raw);
@@ -323,7 +243,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
         // sum I add into FIRST (own) and SECOND (other): tokens I wait on / pass on
         //   own sum:   wait other's second-pass token of the previous digit, pass my first-pass token
         //   other sum: wait other's first-pass token of this digit, pass my second-pass token
-        Token wait_own{tk + 8u * (w == 0 ? 1 : 3), 0u}, wait_oth{tk + 8u * (w == 0 ? 2 : 0), 0u};
+        Token<SUSPEND> wait_own{tk + 8u * (w == 0 ? 1 : 3), 0u}, wait_oth{tk + 8u * (w == 0 ? 2 : 0), 0u};
         const uint32_t pass_own = tk + 8u * (w == 0 ? 0 : 2), pass_oth = tk + 8u * (w == 0 ? 3 : 1);
         const uint32_t tm = *tm_base_s + ((uint32_t)(32 * q) << 16);
         cplx *xb = xb_all + (size_t)warp * XBW;
@@ -386,7 +306,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
             const uint32_t at = live ? at_src[a.step_mode ? 0 : step] : 0u;
             if (at == 0) {                                          // :413 / dead unit: keep the ring moving, compute nothing
                 for (int j = 0; j < 2 * l; j++) {
-                    mbs_wait(full_s + 8u * rp.slot, rp.par);
+                    mbs_wait<SUSPEND>(full_s + 8u * rp.slot, rp.par);
                     __syncwarp();
                     if (t == 0) mbs_arrive(empty_s + 8u * rp.slot);
                     rp.advance(2);
@@ -423,7 +343,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
 #pragma unroll
                 for (int ps = 0; ps < 2; ps++) {
                     const uint32_t tmz = ps == 0 ? tm_tacc : tm + (w == 0 ? TMW_TACC_A : TMW_TACC_B);
-                    mbs_wait(full_s + 8u * rp.slot, rp.par);
+                    mbs_wait<SUSPEND>(full_s + 8u * rp.slot, rp.par);
                     const cplx *kp = ring + (size_t)rp.slot * H + t;
                     if (ps == 0) { if (j > 0) wait_own.wait(); } else wait_oth.wait();
                     tm_fence_after();
@@ -437,17 +357,8 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                         tm_wait_ld();
                         tm_pin16(v[c & 1]);
                         if (c < 7) tm_ld16(tmz + 16 * (c + 1), v[(c + 1) & 1]);
-                        // two sweeps so that consecutive DFMAs share their first source (x.x, then x.y): see bf_group
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const cplx ac = unpack_c(v[c & 1], i), xv = x[4 * c + i];
-                            z[i] = make_double2(fma(xv.x, kc[i].x, ac.x), fma(xv.x, kc[i].y, ac.y));
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const cplx xv = x[4 * c + i];
-                            z[i] = make_double2(fma(-xv.y, kc[i].y, z[i].x), fma(xv.y, kc[i].x, z[i].y));
-                        }
+                        for (int i = 0; i < 4; i++) z[i] = cmac_f(unpack_c(v[c & 1], i), x[4 * c + i], kc[i]);
                         tm_st_c4(tmz + 16 * c, z);
                     }
                     tm_wait_st();

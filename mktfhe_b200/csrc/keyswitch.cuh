@@ -142,15 +142,19 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
 }
-// hardware-suspended wait (try_wait with a time hint); a protocol error traps after 2^22 expired hints instead of hanging the device
+// tight try_wait loop; bounded (trap after 2^28 failed polls) in -DMKTFHE_DEBUG_SPIN builds, see kernels_fast.cuh
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t spins = 0, ok = 0;
-    do {
-        asm volatile("{\n.reg .pred p;\n"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-                     "selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity), "r"(20000u) : "memory");
-        if (!ok && ++spins > (1u << 22)) __trap();
-    } while (!ok);
+#ifdef MKTFHE_DEBUG_SPIN
+    asm volatile("{\n.reg .pred p, q;\n.reg .u32 cnt;\nmov.u32 cnt, 0;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "add.u32 cnt, cnt, 1;\nsetp.gt.u32 q, cnt, 268435456;\n@q trap;\n"
+                 "bra WAIT_%=;\nDONE_%=:\n}" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+#else
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

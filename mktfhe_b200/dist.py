@@ -60,14 +60,23 @@ def broadcast_keys(ks: KeySet | None, p: Params, device, src: int = 0):
     return parties, crs
 
 
-def setup_replicated(p: Params, seed: int, device_index: int, rank: int, world: int, timings: bool = False):
-    """Key generation on rank 0, NCCL broadcast, upload from device memory on every rank.
+def setup_replicated(p: Params, seed: int, device_index: int, rank: int, world: int, timings: bool = False, keygen: str = "host"):
+    """keygen="host": key generation on rank 0 (host library), NCCL broadcast, upload from device memory on every rank.
+    keygen="device": every rank generates the (identical, seed-determined) key set on its own GPU -- nothing crosses PCIe or NVLink.
     Returns (Scheme, KeySet); ranks other than 0 hold secret keys only (for encrypting / checking their shard).
     timings=True appends {"keygen_s", "broadcast_s", "upload_finalize_s", "key_bytes"} (this rank's wall clock)."""
-    from .scheme import Scheme
+    from .scheme import Scheme, setup_generated
     import os
     import time
     t0 = time.perf_counter()
+    if keygen == "device":
+        s, ks = setup_generated(p, seed, device=device_index)
+        if timings:
+            nparties = p.k if p.is_mk else 1
+            nbytes = nparties * sum(int(np.prod(shape)) * np.dtype(dt).itemsize for _, shape, dt in key_arrays(p))
+            return s, ks, {"mode": "device", "keygen_s": time.perf_counter() - t0, "broadcast_s": 0.0, "upload_finalize_s": 0.0, "key_bytes": nbytes,
+                           "note": "evaluation keys generated on each GPU from the seed (csrc/keygen.cuh), byte-identical to the host library's; includes finalize"}
+        return s, ks
     ks = KeySet(p, seed=seed, secret_only=(rank != 0), nthreads=max(1, len(os.sched_getaffinity(0)) // max(1, min(world, 8))) if rank else len(os.sched_getaffinity(0)))
     t1 = t2 = time.perf_counter()
     s = Scheme(p, device_index)
@@ -93,7 +102,7 @@ def setup_replicated(p: Params, seed: int, device_index: int, rank: int, world: 
     if timings:
         nparties = p.k if p.is_mk else 1
         nbytes = nparties * sum(int(np.prod(shape)) * np.dtype(dt).itemsize for _, shape, dt in key_arrays(p))
-        return s, ks, {"keygen_s": t1 - t0, "broadcast_s": (t2 - t1) if world > 1 else 0.0, "upload_finalize_s": time.perf_counter() - t2,
+        return s, ks, {"mode": "host", "keygen_s": t1 - t0, "broadcast_s": (t2 - t1) if world > 1 else 0.0, "upload_finalize_s": time.perf_counter() - t2,
                        "key_bytes": nbytes, "note": "rank 0 generates (host, OpenMP); NCCL broadcast GPU->GPU; upload = device-to-device copy + FAST layouts"}
     return s, ks
 
