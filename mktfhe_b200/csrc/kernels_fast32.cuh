@@ -313,6 +313,256 @@ __global__ void __launch_bounds__(CTA, 1) k_rgsw_tm(const Args a) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tm_base_s));
 }
 
+// setmaxnreg only redistributes the registers the CTA was launched with: 16 x 112 + 4 x 24 <= 20 x 96
+static_assert(16 * 112 + 4 * 24 <= 20 * 96, "setmaxnreg over-subscription");
+// ---- the same kernel with the keys delivered by TMA ----------------------------------------------------------------
+// All gates of a launch use the same key (one party) in the same order, so one key stream serves the eight units of a CTA:
+// a fifth warpgroup issues `cp.async.bulk` copies into a 64 KiB shared-memory ring (the space the RLWE accumulators left
+// when they moved to TMEM) guarded by full/empty mbarriers; the consumers read their key values four at a time right before
+// the multiply-accumulate.  Key-load latency (48 dependent L2 loads per digit in the LMSS fold) leaves the critical path,
+// and the key values no longer occupy 64 registers.  Launched with 20 warps at <= 96 registers and re-split with
+// `setmaxnreg` (producer 24, consumers 112).
+constexpr int RING_BYTES32 = 64 * 1024;
+template <int ELL> struct TileCfg32 { static constexpr int TILE = ELL == 1 ? H : H / 2, RING = RING_BYTES32 / (TILE * 16); };
+constexpr int CTA_TMA32 = CTA + 128;
+constexpr size_t SMEM_BYTES_TMA32 = U * SMEM_UNIT + (size_t)(32 + 256) * 16 + (size_t)RING_BYTES32 + 512;
+
+template <int ELL>
+__global__ void __launch_bounds__(CTA_TMA32, 1) k_rgsw_tma(const Args a) {
+    using fast::mb_init; using fast::mb_expect_tx; using fast::mb_arrive; using fast::mb_wait; using fast::mb_wait_suspend; using fast::bulk_g2s;
+    constexpr int TILE = TileCfg32<ELL>::TILE, RING = TileCfg32<ELL>::RING, PARTS = H / TILE, EP = 8 / PARTS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, unit_l = tid / UT, t = tid % UT;
+    cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + U * SMEM_UNIT), *tw3 = tw2 + 32;
+    cplx *ring = tw3 + 256;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)RING * TILE), *empty = full + RING;
+    uint32_t *tm_base_s = reinterpret_cast<uint32_t *>(empty + RING);
+    for (int i = tid; i < 256; i += CTA_TMA32) { if (i < 32) tw2[i] = a.tb.t2[i]; tw3[i] = a.tb.t3[i]; }
+    if (tid == 0) {
+        for (int s = 0; s < RING; s++) { mb_init(&full[s], 1); mb_init(&empty[s], CTA); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"((uint32_t)__cvta_generic_to_shared(tm_base_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    const int l = a.l, logB = a.logB;
+    const size_t per_idx = (size_t)4 * l * H;
+    const int nsteps = a.step_mode ? 1 : (ELL == 1 ? a.n : a.d);
+    const uint32_t tiles_per_step = (uint32_t)(2 * l * PARTS * ELL * 2);
+    const uint32_t ntiles = (uint32_t)nsteps * tiles_per_step;
+
+    if (warp >= U * 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (tid == CTA) {
+            // tile n = ((((step * 2l + dg) * PARTS + part) * ELL + b) * 2 + comp)
+            for (uint32_t n = 0; n < ntiles; n++) {
+                const int slot = n % RING;
+                if (n >= RING) mb_wait_suspend(&empty[slot], ((n / RING) - 1) & 1);
+                const uint32_t comp = n & 1, b = (n >> 1) % ELL, part = ((n >> 1) / ELL) % PARTS;
+                const uint32_t dg = ((n >> 1) / ELL / PARTS) % (2 * l), step = (n >> 1) / ELL / PARTS / (2 * l);
+                const int idx = (a.step_mode ? a.step_idx : (int)step) * ELL + (int)b;
+                mb_expect_tx(&full[slot], TILE * 16);
+                bulk_g2s(ring + (size_t)slot * TILE, a.brk + (size_t)idx * per_idx + (size_t)(dg * 2 + comp) * H + (size_t)part * TILE, TILE * 16, &full[slot]);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");   // 16 * 112 + 4 * 24 <= 20 * 96: the re-split only redistributes the CTA's own launch allocation
+        cplx *xa = reinterpret_cast<cplx *>(smem_raw + unit_l * SMEM_UNIT), *xc = xa + XB_LEN;
+        // warp w -> lanes 32*(w%4).., columns 96*(w/4)..; per thread: tacc.b [0,32), tacc.a [32,64), acc.b [64,80), acc.a [80,96)
+        const uint32_t tm = *tm_base_s + ((uint32_t)(32 * (warp & 3)) << 16) + 96u * (uint32_t)(warp >> 2);
+        constexpr uint32_t TM_ACCB = 64, TM_ACCA = 80;
+        const size_t unit = (size_t)blockIdx.x * U + unit_l;
+        const bool live = unit < a.units;
+        const size_t gate = live ? unit : 0;
+        uint32_t tile_n = 0;
+        auto tile_wait = [&]() -> const cplx * {
+            const int slot = tile_n % RING;
+            mb_wait(&full[slot], (tile_n / RING) & 1);
+            return ring + (size_t)slot * TILE + t;
+        };
+        auto tile_done = [&]() { mb_arrive(&empty[tile_n % RING]); tile_n++; };
+
+        if (live) {
+            uint32_t vb[16], va[16];
+            if (!a.step_mode) {                    // test vector: bootstrapping.jl:11-23
+                const uint32_t tb = a.tilde[gate * a.lwe_words];
+                const uint32_t e8 = 1u << 29;
+#pragma unroll
+                for (int m = 0; m < 16; m++) {
+                    const uint32_t i1 = (uint32_t)(t + 64 * m) + 1;      // 1-based coefficient index
+                    vb[m] = tb <= (uint32_t)N ? (i1 <= tb ? e8 : 0u - e8) : (i1 <= tb - (uint32_t)N ? 0u - e8 : e8);
+                    va[m] = 0u;
+                }
+            } else {
+                const uint32_t *src = a.acc_io + unit * 2 * N;
+#pragma unroll
+                for (int m = 0; m < 16; m++) { vb[m] = src[t + 64 * m]; va[m] = src[N + t + 64 * m]; }
+            }
+            fast::tm_st16(tm + TM_ACCB, vb);
+            fast::tm_st16(tm + TM_ACCA, va);
+            tm_wait_st();
+        }
+        const int bit = 32 - l * logB;
+        uint32_t cadd = bit > 0 ? 1u << (bit - 1) : 0u;                 // divbits rounding (arithmetic.jl:23-27)
+        for (int j = 0; j < l; j++) cadd += 1u << (bit + j * logB + logB - 1);   // + B/2 at every digit position (gsw.jl:86-96)
+        const uint32_t mask = (1u << logB) - 1;
+        const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));
+        const uint32_t *at_src = a.step_mode ? a.tilde + gate * ELL : a.tilde + gate * a.lwe_words + 1;
+        const int brv6t = (int)(__brev((unsigned)t) >> 26);
+
+        for (int step = 0; step < nsteps; step++) {
+            uint32_t atv[ELL];
+            bool any = false;
+#pragma unroll
+            for (int b = 0; b < ELL; b++) { atv[b] = live ? at_src[(a.step_mode ? 0 : step * ELL) + b] : 0u; any |= atv[b] > 0; }
+            if (!any) {                                                   // :48 / whole-block no-op / dead unit: keep the ring moving
+                for (uint32_t i = 0; i < tiles_per_step; i++) { tile_wait(); tile_done(); }
+                continue;
+            }
+            // slot n = 8t + e evaluates at exp(-i*pi*(4*brv9(n)+1)/N), brv9(n) = 64*brv3(e) + brv6(t)
+            cplx m1v[ELL];
+#pragma unroll
+            for (int b = 0; b < ELL; b++) m1v[b] = __ldg(&a.tb.emono[((4 * brv6t + 1) * atv[b]) & 2047]);
+
+            for (int dg = 0; dg < 2 * l; dg++) {
+                const int sh = bit + (l - 1 - (dg < l ? dg : dg - l)) * logB;
+                cplx x[8];
+                {
+                    uint32_t v[16];
+                    fast::tm_ld16(tm + (dg < l ? TM_ACCB : TM_ACCA), v);
+                    tm_wait_ld();
+                    fast::tm_pin16(v);
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        const uint32_t f0 = ((v[m] + cadd) >> sh) & mask, f1 = ((v[m + 8] + cadd) >> sh) & mask;
+                        x[m] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
+                    }
+                }
+                fft_fwd(x, xa, xc, tw2, tw3, t, unit_l, []() {});
+#pragma unroll
+                for (int part = 0; part < PARTS; part++) {
+                    cplx kcb[EP], kca[EP];
+                    if (ELL == 1) {
+                        const cplx *kb = tile_wait();
+                        const int slot_b = tile_n % RING;
+                        tile_n++;                                   // hold the .b tile while the .a tile is awaited
+                        const cplx *ka = tile_wait();
+#pragma unroll
+                        for (int e = 0; e < EP; e++) { kcb[e] = kb[e * UT]; kca[e] = ka[e * UT]; }
+                        mb_arrive(&empty[slot_b]);
+                        tile_done();
+                    } else {
+                        // block (LMSS): fold the monomials of the block's key bits into the keys,
+                        //   sum_bit mono_bit * (sum_dg D_dg * K_bit,dg) = sum_dg D_dg * (sum_bit mono_bit * K_bit,dg)
+#pragma unroll
+                        for (int e = 0; e < EP; e++) kcb[e] = kca[e] = make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int b = 0; b < ELL; b++) {
+                            const cplx *kb = tile_wait();
+                            const int slot_b = tile_n % RING;
+                            tile_n++;
+                            const cplx *ka = tile_wait();
+                            if (atv[b] != 0) {
+#pragma unroll
+                                for (int eh = 0; eh < EP; eh++) {
+                                    const int e = EP * part + eh;
+                                    const int b3 = ((e & 1) << 2) | (e & 2) | ((e & 4) >> 2);
+                                    cplx mo = cmul_f(m1v[b], c_e16[((atv[b] * b3) & 7) * 2]);
+                                    mo.x -= 1.0 / H;
+                                    kcb[eh] = cmac_f(kcb[eh], mo, kb[eh * UT]);
+                                    kca[eh] = cmac_f(kca[eh], mo, ka[eh * UT]);
+                                }
+                            }
+                            mb_arrive(&empty[slot_b]);
+                            tile_done();
+                        }
+                    }
+#pragma unroll
+                    for (int c2 = 0; c2 < EP / 4; c2++) {
+                        const int c = (EP / 4) * part + c2;
+                        cplx zb[4], za[4];
+                        if (dg == 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) { zb[i] = cmul_f(x[4 * c + i], kcb[4 * c2 + i]); za[i] = cmul_f(x[4 * c + i], kca[4 * c2 + i]); }
+                        } else {
+                            uint32_t rb[16], ra[16];
+                            fast::tm_ld16(tm + 16 * c, rb);
+                            fast::tm_ld16(tm + 32 + 16 * c, ra);
+                            tm_wait_ld();
+                            fast::tm_pin16(rb); fast::tm_pin16(ra);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                zb[i] = make_double2(__hiloint2double((int)rb[4 * i + 1], (int)rb[4 * i]), __hiloint2double((int)rb[4 * i + 3], (int)rb[4 * i + 2]));
+                                za[i] = make_double2(__hiloint2double((int)ra[4 * i + 1], (int)ra[4 * i]), __hiloint2double((int)ra[4 * i + 3], (int)ra[4 * i + 2]));
+                                zb[i] = cmac_f(zb[i], x[4 * c + i], kcb[4 * c2 + i]); za[i] = cmac_f(za[i], x[4 * c + i], kca[4 * c2 + i]);
+                            }
+                        }
+                        fast::tm_st_c4(tm + 16 * c, zb);
+                        fast::tm_st_c4(tm + 32 + 16 * c, za);
+                    }
+                }
+                tm_wait_st();
+            }
+            // both outputs: (x (X^a - 1)/H for ELL == 1) -> inverse transform -> round -> acc +=
+#pragma unroll 1
+            for (int pz = 0; pz < 2; pz++) {
+                cplx y[8];
+                {
+                    uint32_t v[2][16];
+                    fast::tm_ld16(tm + 32 * pz, v[0]); fast::tm_ld16(tm + 32 * pz + 16, v[1]);
+                    tm_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        fast::tm_pin16(v[c]);
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            y[4 * c + i] = make_double2(__hiloint2double((int)v[c][4 * i + 1], (int)v[c][4 * i]), __hiloint2double((int)v[c][4 * i + 3], (int)v[c][4 * i + 2]));
+                    }
+                }
+                if (ELL == 1) {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int b3 = ((e & 1) << 2) | (e & 2) | ((e & 4) >> 2);
+                        cplx mo = cmul_f(m1v[0], c_e16[((atv[0] * b3) & 7) * 2]);      // 8th roots = even 16th roots
+                        mo.x -= 1.0 / H;
+                        y[e] = cmul_f(mo, y[e]);
+                    }
+                }
+                fft_inv(y, xa, xc, tw2, tw3, t, unit_l);
+                {
+                    uint32_t v[16];
+                    fast::tm_ld16(tm + (pz == 0 ? TM_ACCB : TM_ACCA), v);
+                    tm_wait_ld();
+                    fast::tm_pin16(v);
+#pragma unroll
+                    for (int m = 0; m < 8; m++) { v[m] += d2torus32(y[m].x); v[m + 8] += d2torus32(-y[m].y); }
+                    fast::tm_st16(tm + (pz == 0 ? TM_ACCB : TM_ACCA), v);
+                    tm_wait_st();
+                }
+            }
+        }
+        if (live) {
+            uint32_t *out = a.acc_io + unit * 2 * N;
+            uint32_t vb[16], va[16];
+            fast::tm_ld16(tm + TM_ACCB, vb);
+            fast::tm_ld16(tm + TM_ACCA, va);
+            tm_wait_ld();
+            fast::tm_pin16(vb); fast::tm_pin16(va);
+#pragma unroll
+            for (int m = 0; m < 16; m++) { out[t + 64 * m] = vb[m]; out[N + t + 64 * m] = va[m]; }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(*tm_base_s));
+}
+
+
 // reference slot order [poly][8t + e] -> thread order [poly][e][t]
 __global__ void k_permute_brk(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -388,6 +638,8 @@ static inline int fast32_build(FastKeys32 &f, const mktfhe_params &p, const cplx
     }
     FCK(cudaFuncSetAttribute(k_rgsw_tm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     FCK(cudaFuncSetAttribute(k_rgsw_tm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    FCK(cudaFuncSetAttribute(k_rgsw_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TMA32));
+    FCK(cudaFuncSetAttribute(k_rgsw_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_TMA32));
     f.built = true;
     return 0;
 }
@@ -398,7 +650,17 @@ static inline int fast32_launch(FastKeys32 &f, const mktfhe_params &p, fast32::A
     a.brk = f.brk; a.tb = Tables{f.t2, f.t3, f.emono};
     a.n = p.n; a.d = p.d; a.l = p.l_gsw; a.logB = p.logB_gsw; a.lwe_words = (int)mktfhe_lwe_words(&p);
     const unsigned grid = (unsigned)((a.units + U - 1) / U);
-    if (p.scheme == MKTFHE_LMSS && !(a.step_mode == 1)) k_rgsw_tm<3><<<grid, CTA, SMEM_BYTES, stream>>>(a);
+    // Keys by per-thread loads (k_rgsw_tm) or through a TMA ring shared by the CTA's eight gates (k_rgsw_tma).  Measured on B200,
+    // 4096 gates: LMSS 78.7 ms -> 31.6 ms with the ring (its 48 dependent key loads per digit leave the critical path), CGGI
+    // 47.1 ms -> 55.1 ms (one key tile per digit: the ring's mbarrier round trips cost more than the loads they replace).
+    // Default: ring for LMSS, per-thread loads for CGGI; MKTFHE_FAST32_KERNEL = tmem | tma forces one for both (A/B runs).
+    static const int force = []() { const char *e = getenv("MKTFHE_FAST32_KERNEL"); return !e ? 0 : std::string(e) == "tma" ? 1 : std::string(e) == "tmem" ? 2 : 0; }();
+    const bool blk = p.scheme == MKTFHE_LMSS && !(a.step_mode == 1);
+    const bool tma = force == 1 || (force == 0 && blk);
+    if (tma) {
+        if (blk) k_rgsw_tma<3><<<grid, CTA_TMA32, SMEM_BYTES_TMA32, stream>>>(a);
+        else k_rgsw_tma<1><<<grid, CTA_TMA32, SMEM_BYTES_TMA32, stream>>>(a);
+    } else if (blk) k_rgsw_tm<3><<<grid, CTA, SMEM_BYTES, stream>>>(a);
     else k_rgsw_tm<1><<<grid, CTA, SMEM_BYTES, stream>>>(a);
     if (launches) (*launches)++;
     FCK(cudaGetLastError());

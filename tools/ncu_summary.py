@@ -23,7 +23,9 @@ KEEP = [
 
 
 def main(rep, out):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    # accepts the report itself or its `--page raw --csv` export (the GPU job exports on the box and drops the large report)
+    raw = open(rep).read() if rep.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     names, units, vals = rows[0], rows[1], rows[2]
     col = {n: i for i, n in enumerate(names)}
