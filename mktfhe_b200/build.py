@@ -19,7 +19,8 @@ INCLUDE = os.path.join(ROOT, "include")
 LIBDIR = os.path.join(PKG, "lib")
 
 HOST_LIB = os.path.join(LIBDIR, "libmktfhe_host.so")
-CUDA_LIB = os.path.join(LIBDIR, "libmktfhe_b200.so")
+# MKTFHE_CUDA_LIB: load / build another copy of the CUDA library (A/B and knock-out timing variants built with MKTFHE_NVCC_EXTRA)
+CUDA_LIB = os.environ.get("MKTFHE_CUDA_LIB") or os.path.join(LIBDIR, "libmktfhe_b200.so")
 
 HOST_SRCS = ["host_keygen.cpp"]
 CUDA_SRCS = ["capi.cu"]
@@ -82,8 +83,9 @@ def build_cuda(force: bool = False) -> str:
         tmp = CUDA_LIB + ".tmp"
         # MKTFHE_DEBUG_SPIN=1: every mbarrier wait is bounded and traps instead of hanging (csrc/kernels_fast.cuh)
         dbg = ["-DMKTFHE_DEBUG_SPIN"] if os.environ.get("MKTFHE_DEBUG_SPIN") == "1" else []
+        dbg += os.environ.get("MKTFHE_NVCC_EXTRA", "").split()
         _run([nvcc_path()] + NVCC_FLAGS + dbg + ["-I", INCLUDE, "-o", tmp] + srcs + ["-lquadmath"],
-             log=os.path.join(LIBDIR, "nvcc_build.log"))
+             log=CUDA_LIB + ".nvcc.log" if os.environ.get("MKTFHE_CUDA_LIB") else os.path.join(LIBDIR, "nvcc_build.log"))
         os.replace(tmp, CUDA_LIB)
     return CUDA_LIB
 

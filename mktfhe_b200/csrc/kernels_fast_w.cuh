@@ -36,7 +36,13 @@ constexpr int WU = 4;                       // units per CTA = TMEM lane quadran
 constexpr int NCW = 2 * WU;                 // consumer warps
 constexpr int CTA_W = NCW * 32 + 128;       // + producer warpgroup (setmaxnreg works on warpgroups)
 constexpr int XBW = H + 32;                 // exchange buffer: element n at n + (n >> 5)
-constexpr int RINGW = 5;                    // key tiles (16 KiB polynomials) in flight
+#ifndef W_RING
+#define W_RING 5
+#endif
+constexpr int RINGW = W_RING;               // key tiles (16 KiB polynomials) in flight
+#ifndef W_FIRST_STORE
+#define W_FIRST_STORE 1
+#endif
 constexpr int W_LAUNCH_REGS = 168, W_CONSUMER_REGS = 232, W_PRODUCER_REGS = 24;
 static_assert(NCW * W_CONSUMER_REGS + 4 * W_PRODUCER_REGS <= (CTA_W / 32) * W_LAUNCH_REGS, "setmaxnreg over-subscription");
 constexpr size_t SMEM_BYTES_W = ((size_t)NCW * XBW + 512 + (size_t)RINGW * H) * 16 + (2 * RINGW + 4 * WU) * 8 + 16;
@@ -83,7 +89,11 @@ __device__ __forceinline__ void pass1_inv(cplx (&x)[32]) {
 // register sources, run time unchanged within noise.)
 __device__ __forceinline__ void pass2_fwd(cplx (&x)[32], const cplx *__restrict__ tw) {
     {
+#ifdef KO_TW2CONST
+        const cplx w = c_tw1w[1];
+#else
         const cplx w = tw[0];
+#endif
 #pragma unroll
         for (int e = 0; e < 16; e++) bf(x[e], x[e + 16], w);
     }
@@ -94,7 +104,11 @@ __device__ __forceinline__ void pass2_fwd(cplx (&x)[32], const cplx *__restrict_
             const int half = 16 >> (s - 5);
             if (e & half) continue;
             const int sub = e >> (10 - s);
+#ifdef KO_TW2CONST
+            const cplx w = c_tw1w[((1 << (s - 6)) + (sub >> 1))];
+#else
             const cplx w = tw[((1 << (s - 6)) + (sub >> 1)) * 32];
+#endif
             if (sub & 1) bf_mi(x[e], x[e + half], w); else bf(x[e], x[e + half], w);
         }
     }
@@ -107,12 +121,20 @@ __device__ __forceinline__ void pass2_inv(cplx (&x)[32], const cplx *__restrict_
             const int half = 16 >> (s - 5);
             if (e & half) continue;
             const int sub = e >> (10 - s);
+#ifdef KO_TW2CONST
+            const cplx w = c_tw1w[((1 << (s - 6)) + (sub >> 1))];
+#else
             const cplx w = tw[((1 << (s - 6)) + (sub >> 1)) * 32];
+#endif
             if (sub & 1) bi_mi(x[e], x[e + half], w); else bi(x[e], x[e + half], w);
         }
     }
     {
+#ifdef KO_TW2CONST
+        const cplx w = c_tw1w[1];
+#else
         const cplx w = tw[0];
+#endif
 #pragma unroll
         for (int e = 0; e < 16; e++) bi(x[e], x[e + 16], w);
     }
@@ -120,21 +142,25 @@ __device__ __forceinline__ void pass2_inv(cplx (&x)[32], const cplx *__restrict_
 __device__ __forceinline__ void fft_fwd(cplx (&x)[32], cplx *xb, const cplx *tw, int t) {
     pass1_fwd(x);
     __syncwarp();                                       // earlier readers of xb are done
+#ifndef KO_XCHG                                         // KO_*: knock-out timing variants (wrong results), profiles/README_r2.md
 #pragma unroll
     for (int m = 0; m < 32; m++) xb[t + 33 * m] = x[m];
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < 32; e++) x[e] = xb[33 * t + e];
+#endif
     pass2_fwd(x, tw);
 }
 __device__ __forceinline__ void fft_inv(cplx (&x)[32], cplx *xb, const cplx *tw, int t) {
     pass2_inv(x, tw);
     __syncwarp();
+#ifndef KO_XCHG
 #pragma unroll
     for (int e = 0; e < 32; e++) xb[33 * t + e] = x[e];
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 32; m++) x[m] = xb[t + 33 * m];
+#endif
     pass1_inv(x);
 }
 
@@ -162,11 +188,17 @@ __device__ __forceinline__ void mbs_arrive(uint32_t bar) { asm volatile("mbarrie
 template <int SUSPEND> struct Token {
     uint32_t bar;          // shared-window address
     uint32_t par;
+#ifdef KO_TOKENS
+    __device__ __forceinline__ void wait() {}
+#else
     __device__ __forceinline__ void wait() { mbs_wait<SUSPEND>(bar, par); par ^= 1; }
+#endif
 };
 __device__ __forceinline__ void token_pass(uint32_t bar, int t) {     // all lanes' TMEM stores are complete (tcgen05.wait::st)
     __syncwarp();
+#ifndef KO_TOKENS
     if (t == 0) mbs_arrive(bar);
+#endif
 }
 // ring position of a consumer warp: tile -> (slot, phase parity), advanced without divisions
 struct RingPos {
@@ -257,7 +289,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
         uint64_t cadd = (uint64_t)1 << (64 - l * a.logB - 1);
         for (int j = 0; j < l; j++) cadd += (uint64_t)1 << (64 - l * a.logB + j * a.logB + a.logB - 1);
         if (live) {                                                // each warp initialises its half of the RLWE accumulator (+ cadd) and of the sums
-            {
+            if (!W_FIRST_STORE) {
                 uint32_t z[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) z[i] = 0u;
@@ -297,6 +329,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
         // off again when the accumulator leaves the kernel.
         const uint32_t mask = (1u << logB) - 1;
         const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));
+        const int hB = 1 << (logB - 1);
         const uint32_t *at_src = a.step_mode ? a.tilde + up : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
         const int brv5t = (int)(__brev((unsigned)t) >> 27);
         // this warp consumes every second tile of the producer's sequence, starting at tile w
@@ -333,7 +366,12 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                             const uint64_t v1 = ((uint64_t)v[c][4 * i + 3] << 32) | v[c][4 * i + 2];
                             const uint32_t f0 = (uint32_t)(v0 >> sh) & mask, f1 = (uint32_t)(v1 >> sh) & mask;
                             // signed(d_j) - im*signed(d_{j+H}); 2^52 + field is exact in the double's mantissa
+#ifdef W_DECOMP_I2F
+                            // conversion unit instead of the FP64 pipe (one I2F against one DADD per coefficient)
+                            x[16 * hb + 4 * c + i] = make_double2(__int2double_rn((int)f0 - hB), __int2double_rn(hB - (int)f1));
+#else
                             x[16 * hb + 4 * c + i] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
+#endif
                         }
                     }
                 }
@@ -347,18 +385,30 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                     const cplx *kp = ring + (size_t)rp.slot * H + t;
                     if (ps == 0) { if (j > 0) wait_own.wait(); } else wait_oth.wait();
                     tm_fence_after();
+                    // The first addition of a step into a sum is its owner's (ps == 0, j == 0) and follows the owner's own read of the
+                    // previous step's sum in program order: it stores x * key instead of accumulating, so the sums are never cleared.
+                    const bool first = W_FIRST_STORE && ps == 0 && j == 0;
                     uint32_t v[2][16];
-                    tm_ld16(tmz, v[0]);
+                    if (!first) tm_ld16(tmz, v[0]);
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
                         cplx kc[4], z[4];
 #pragma unroll
+#ifdef KO_KEYLDS
+                        for (int i = 0; i < 4; i++) kc[i] = c_tw1w[(4 * c + i) & 31];
+#else
                         for (int i = 0; i < 4; i++) kc[i] = kp[(4 * c + i) * 32];
-                        tm_wait_ld();
-                        tm_pin16(v[c & 1]);
-                        if (c < 7) tm_ld16(tmz + 16 * (c + 1), v[(c + 1) & 1]);
+#endif
+                        if (first) {
 #pragma unroll
-                        for (int i = 0; i < 4; i++) z[i] = cmac_f(unpack_c(v[c & 1], i), x[4 * c + i], kc[i]);
+                            for (int i = 0; i < 4; i++) z[i] = cmul_f(x[4 * c + i], kc[i]);
+                        } else {
+                            tm_wait_ld();
+                            tm_pin16(v[c & 1]);
+                            if (c < 7) tm_ld16(tmz + 16 * (c + 1), v[(c + 1) & 1]);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) z[i] = cmac_f(unpack_c(v[c & 1], i), x[4 * c + i], kc[i]);
+                        }
                         tm_st_c4(tmz + 16 * c, z);
                     }
                     tm_wait_st();
@@ -386,7 +436,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                         for (int i = 0; i < 4; i++) y[16 * hb + 4 * c + i] = unpack_c(v[c], i);
                     }
                 }
-                {   // clear the sums for the next step (every product accumulates, also the first)
+                if (!W_FIRST_STORE) {   // clear the sums for the next step (every product accumulates, also the first)
                     uint32_t z[16];
 #pragma unroll
                     for (int i = 0; i < 16; i++) z[i] = 0u;
