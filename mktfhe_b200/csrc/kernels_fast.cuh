@@ -987,7 +987,11 @@ __global__ void __launch_bounds__(CTA_TMA, 1) k_phase1_tma(const Args a) {
         if (tid == CTA) {
             for (uint32_t n = 0; n < ntiles; n++) {
                 const int slot = n % RING;
+#ifdef TMA_PRODUCER_SPIN
+                if (n >= RING) mb_wait(&empty[slot], ((n / RING) - 1) & 1);
+#else
                 if (n >= RING) mb_wait_suspend(&empty[slot], ((n / RING) - 1) & 1);
+#endif
                 // tile n = ((((step * 2l + dg) * HALVES + half) * ELL + b) * 2 + comp)
                 const uint32_t comp = n & 1, b = (n >> 1) % ELL, hf = ((n >> 1) / ELL) % HALVES;
                 const uint32_t dg = ((n >> 1) / ELL / HALVES) % (2 * l), step = (n >> 1) / ELL / HALVES / (2 * l);
@@ -1660,7 +1664,19 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
     for (int j = 0; j < 16; j++) { const __float128 ang = pi * j / 8; e16[j] = make_double2((double)cosq(ang), (double)-sinq(ang)); }
     for (int i = 1; i < 16; i++) tw1[i] = tw[i];
     {   // one-warp transform (kernels_fast_w.cuh): stages 1..5 in the constant bank, stages 6..10 per thread [16][32]
-        std::vector<cplx> tw1w(32, make_double2(0.0, 0.0)), e32(32), t2w(512);
+        // t2w: [16][32] forward pass 2 | [16][32] inverse (decimation in time) stages 5..9 | untwist exp(i*pi*k/2048), k = 0..512
+        std::vector<cplx> tw1w(32, make_double2(0.0, 0.0)), e32(32), t2w(512 + 512 + 514, make_double2(0.0, 0.0)), w32i(16);
+        auto unit = [&](__float128 num, __float128 den) { const __float128 ang = 2 * pi * num / den; return make_double2((double)cosq(ang), (double)sinq(ang)); };
+        for (int j = 0; j < 16; j++) w32i[j] = unit(j, 32);
+        for (int t = 0; t < 32; t++) {
+            cplx *ti = t2w.data() + 512;
+            ti[t] = unit(t, 64);
+            ti[32 + t] = unit(t, 128);
+            for (int g = 0; g < 2; g++) ti[(2 + g) * 32 + t] = unit(t + 32 * g, 256);
+            for (int g = 0; g < 4; g++) ti[(4 + g) * 32 + t] = unit(t + 32 * g, 512);
+            for (int g = 0; g < 8; g++) ti[(8 + g) * 32 + t] = unit(t + 32 * g, 1024);
+        }
+        for (int k = 0; k <= 512; k++) t2w[1024 + k] = unit(k, 4096);
         for (int i = 1; i < 32; i++) tw1w[i] = tw[i];
         for (int j = 0; j < 32; j++) { const __float128 ang = pi * j / 16; e32[j] = make_double2((double)cosq(ang), (double)-sinq(ang)); }
         for (int t = 0; t < 32; t++) {
@@ -1670,8 +1686,9 @@ static inline int fast_build(FastKeys &f, const mktfhe_params &p, const std::vec
             for (int g = 0; g < 4; g++) t2w[(4 + g) * 32 + t] = tw[256 + 8 * t + 2 * g];
             for (int g = 0; g < 8; g++) t2w[(8 + g) * 32 + t] = tw[512 + 16 * t + 2 * g];
         }
-        FCK(cudaMalloc(&f.t2w, sizeof(cplx) * 512));
-        FCK(cudaMemcpy(f.t2w, t2w.data(), sizeof(cplx) * 512, cudaMemcpyHostToDevice));
+        FCK(cudaMalloc(&f.t2w, sizeof(cplx) * t2w.size()));
+        FCK(cudaMemcpy(f.t2w, t2w.data(), sizeof(cplx) * t2w.size(), cudaMemcpyHostToDevice));
+        FCK(cudaMemcpyToSymbol(fastw::c_w32i, w32i.data(), sizeof(cplx) * 16));
         FCK(cudaMemcpyToSymbol(fastw::c_tw1w, tw1w.data(), sizeof(cplx) * 32));
         FCK(cudaMemcpyToSymbol(fastw::c_e32, e32.data(), sizeof(cplx) * 32));
         FCK(cudaFuncSetAttribute(fastw::k_phase1_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fastw::SMEM_BYTES_W));
