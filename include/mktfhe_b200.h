@@ -167,6 +167,11 @@ int mktfhe_block_step_batch(mktfhe_ctx *ctx, int party, int blk, const uint32_t 
  *   of w, :538-550).  Lets a test feed the oracle's intermediate polynomials into single products of phase 2. */
 int mktfhe_gadget_product_batch(mktfhe_ctx *ctx, int l, int logB, const uint64_t *polys, const double *keys, int ncomp,
                                 uint64_t *out, size_t batch);
+/* The same for the Torus32 schemes (N = 1024; polys / out uint32, l * logB <= 32): the shape of the CCS hybrid product's sums
+ * (bootstrapping.jl:277-294 u_c / v_c from an accumulator component against d[j] and crs[j] | b[j], :313-320 w from v against f[j]),
+ * built from the device functions of fast32::k_ccs_fast. */
+int mktfhe_gadget_product32_batch(mktfhe_ctx *ctx, int l, int logB, const uint32_t *polys, const double *keys, int ncomp,
+                                  uint32_t *out, size_t batch);
 /* fftto! / ifftto! (fft.jl:57-63,74-81) and poly decompto! (gsw.jl:86-96) on `batch` polynomials.
  * bits = 32 / 64 selects the torus; spectra in the reference's slot order; STRICT arithmetic. */
 int mktfhe_fft_batch(mktfhe_ctx *ctx, int bits, const void *polys, double *spectra, size_t batch);

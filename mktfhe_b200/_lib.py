@@ -19,7 +19,7 @@ EXPORTS = [
     "mktfhe_decomp_batch", "mktfhe_last_stage_ms", "mktfhe_measure_dfma_peak",
     "mktfhe_wires_resize", "mktfhe_wires_write", "mktfhe_wires_read", "mktfhe_gate_level",
     "mktfhe_ctx_create_multi", "mktfhe_ctx_devices",
-    "mktfhe_gadget_product_batch", "mktfhe_keygen_common", "mktfhe_keygen_party", "mktfhe_download_party_key",
+    "mktfhe_gadget_product_batch", "mktfhe_gadget_product32_batch", "mktfhe_keygen_common", "mktfhe_keygen_party", "mktfhe_download_party_key",
 ]
 
 
@@ -40,6 +40,7 @@ def lib() -> ctypes.CDLL:
     L.mktfhe_keygen_party.argtypes = [vp, i32, ctypes.c_uint64, vp]
     L.mktfhe_download_party_key.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mktfhe_gadget_product_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, sz]
+    L.mktfhe_gadget_product32_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, sz]
     L.mktfhe_ctx_destroy.argtypes = [vp]
     L.mktfhe_ctx_destroy.restype = None
     L.mktfhe_last_error.argtypes = [vp]

@@ -1294,6 +1294,35 @@ int mktfhe_gadget_product_batch(mktfhe_ctx *ctx, int l, int logB, const uint64_t
     return rc;
 }
 
+int mktfhe_gadget_product32_batch(mktfhe_ctx *ctx, int l, int logB, const uint32_t *polys, const double *keys, int ncomp, uint32_t *out, size_t batch) {
+    int rc;
+    if (!ctx) return MKTFHE_ERR_ARG;
+    SINGLE_ONLY(ctx, "mktfhe_gadget_product32_batch");
+    if ((rc = check_ready(ctx))) return rc;
+    if (ctx->N != 1024 || !ctx->fast32.t2) return fail(ctx, MKTFHE_ERR_PARAMS, "the 32-bit gadget product hook exists for the FAST N = 1024 paths (CGGI, LMSS, CCS) only");
+    if (!polys || !keys || !out || l < 1 || l > MK_MAXL || logB < 1 || l * logB > 32 || ncomp < 1 || ncomp > 3) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
+    if (batch == 0) return 0;
+    uint32_t *d_in = nullptr, *d_out = nullptr; cplx *d_keys = nullptr;
+    const size_t nk = (size_t)l * ncomp * ctx->H;
+    auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(d_keys); };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_in, batch * ctx->N * 4)) != cudaSuccess || (e = cudaMalloc(&d_out, batch * ncomp * ctx->N * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&d_keys, nk * sizeof(cplx))) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_in, polys, batch * ctx->N * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_keys, keys, nk * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, MKTFHE_ERR_CUDA, cudaGetErrorString(e));
+    }
+    rc = fast32_gadget_product(ctx->fast32, d_in, d_keys, d_out, l, logB, ncomp, batch, ctx->stream, &ctx->launches, ctx->err);
+    if (!rc) {
+        if ((e = cudaMemcpyAsync(out, d_out, batch * ncomp * ctx->N * 4, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+            rc = fail(ctx, MKTFHE_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cleanup();
+    return rc;
+}
+
 int mktfhe_measure_dfma_peak(mktfhe_ctx *ctx, double *tflops_out) {
     if (!ctx || !tflops_out) return MKTFHE_ERR_ARG;
     if (is_multi(ctx)) return mktfhe_measure_dfma_peak(ctx->children[0], tflops_out);

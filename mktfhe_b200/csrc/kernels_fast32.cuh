@@ -817,6 +817,64 @@ __global__ void __launch_bounds__(CCTA, 1) k_ccs_fast(const CcsArgs a) {
     }
 }
 
+// ---- gadget product hook: the building block of the FAST CCS hybrid product on caller-supplied inputs ---------------------------
+// out[c] = native(ifft( Sum_j fft(D_j(poly)) (.) key[j][c] ))  for c < ncomp, with the SAME device functions k_ccs_fast is made of
+// (field-extraction digits, fft_fwd, multiply-accumulate, fft_inv, d2torus32).  The hybrid product re-decomposes a computed
+// polynomial (v) inside one step, so whole-step coefficients cannot be compared between two roundings; this hook lets a test feed the
+// ORACLE's intermediate polynomial into one product and compare within a per-product tolerance
+// (bootstrapping.jl:277-294 u_c / v_c from an accumulator component, :313-320 w from v).  keys: [l][ncomp][H] in the reference slot order.
+struct Gp32Args {
+    const uint32_t *polys;      // [B][N]
+    const cplx *keys;           // [l][ncomp][H]
+    uint32_t *out;              // [B][ncomp][N]
+    Tables tb;
+    int l, logB, ncomp;
+    size_t units;
+};
+__global__ void __launch_bounds__(CCTA, 1) k_gadget_product32(const Gp32Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, unit_l = tid / UT, t = tid % UT;
+    cplx *tw2 = reinterpret_cast<cplx *>(smem_raw + CU * CCS_SMEM_UNIT), *tw3 = tw2 + 32;
+    for (int i = tid; i < 256; i += CCTA) { if (i < 32) tw2[i] = a.tb.t2[i]; tw3[i] = a.tb.t3[i]; }
+    cplx *xa = reinterpret_cast<cplx *>(smem_raw + unit_l * CCS_SMEM_UNIT), *xc = xa + XB_LEN;
+    __syncthreads();
+    const size_t unit = (size_t)blockIdx.x * CU + unit_l;
+    if (unit >= a.units) return;                    // the transforms below synchronise per unit only
+    const int l = a.l, logB = a.logB, bit = 32 - l * logB;
+    uint32_t cadd = bit > 0 ? 1u << (bit - 1) : 0u;
+    for (int j = 0; j < l; j++) cadd += 1u << (bit + j * logB + logB - 1);
+    const uint32_t mask = (1u << logB) - 1;
+    const double dbias = 4503599627370496.0 + (double)(1 << (logB - 1));
+    uint32_t cf[16];
+    const uint32_t *src = a.polys + unit * N;
+#pragma unroll
+    for (int m = 0; m < 8; m++) { cf[m] = src[t + 64 * m]; cf[m + 8] = src[t + 64 * m + H]; }
+    for (int c = 0; c < a.ncomp; c++) {
+        cplx acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[e] = make_double2(0.0, 0.0);
+        for (int j = 0; j < l; j++) {
+            const int sh = bit + (l - 1 - j) * logB;
+            cplx x[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const uint32_t f0 = ((cf[m] + cadd) >> sh) & mask, f1 = ((cf[m + 8] + cadd) >> sh) & mask;
+                x[m] = make_double2(__hiloint2double(0x43300000, (int)f0) - dbias, dbias - __hiloint2double(0x43300000, (int)f1));
+            }
+            fft_fwd(x, xa, xc, tw2, tw3, t, unit_l, []() {});
+            const cplx *k = a.keys + ((size_t)j * a.ncomp + c) * H + 8 * t;           // slot 8t + e
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc[e] = cmac_f(acc[e], x[e], k[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[e] = make_double2(acc[e].x * (1.0 / H), acc[e].y * (1.0 / H));
+        fft_inv(acc, xa, xc, tw2, tw3, t, unit_l);
+        uint32_t *dst = a.out + (unit * a.ncomp + c) * N;
+#pragma unroll
+        for (int m = 0; m < 8; m++) { dst[t + 64 * m] = d2torus32(acc[m].x); dst[t + 64 * m + H] = d2torus32(-acc[m].y); }
+    }
+}
+
 // reference slot order -> thread order, with an optional scale (1/H for the keys that feed an inverse transform)
 __global__ void k_permute_scale(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys, double scale) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -870,6 +928,20 @@ static inline int fastccs_build(FastCcsKeys &f, const mktfhe_params &p, const st
     FCK(cudaMemcpy(f.d_pubb, f.pubb.data(), sizeof(cplx *) * f.pubb.size(), cudaMemcpyHostToDevice));
     FCK(cudaFuncSetAttribute(k_ccs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CCS_SMEM_BYTES));
     f.built = true;
+    return 0;
+}
+
+static inline int fast32_gadget_product(FastKeys32 &tabs, const uint32_t *polys, const cplx *keys, uint32_t *out, int l, int logB, int ncomp,
+                                        size_t batch, cudaStream_t stream, int *launches, std::string &err) {
+    using namespace fast32;
+    if (!tabs.t2) { err = "FAST (N = 1024) tables not built"; return -3; }
+    Gp32Args a{};
+    a.polys = polys; a.keys = keys; a.out = out; a.tb = Tables{tabs.t2, tabs.t3, tabs.emono};
+    a.l = l; a.logB = logB; a.ncomp = ncomp; a.units = batch;
+    FCK(cudaFuncSetAttribute(k_gadget_product32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CCS_SMEM_BYTES));
+    k_gadget_product32<<<(unsigned)((batch + CU - 1) / CU), CCTA, CCS_SMEM_BYTES, stream>>>(a);
+    if (launches) (*launches)++;
+    FCK(cudaGetLastError());
     return 0;
 }
 

@@ -243,13 +243,15 @@ class Scheme:
         return rows
 
     def gadget_product(self, polys, keys, l, logB):
-        """out[g][c] = native(ifft(Sum_j fft(D_j(polys[g])) * keys[j][c])): one product of FAST phase 2 (KMS*)."""
-        polys = np.ascontiguousarray(polys, dtype=np.uint64)
+        """out[g][c] = native(ifft(Sum_j fft(D_j(polys[g])) * keys[j][c])): one product of FAST phase 2 (KMS*, Torus64) or of the FAST
+        CCS hybrid product (N = 1024, Torus32)."""
+        dt = self.torus_dtype
+        polys = np.ascontiguousarray(polys, dtype=dt)
         keys = np.ascontiguousarray(keys, dtype=np.float64)            # [l][ncomp][H][2]
         assert keys.shape[0] == l and keys.shape[2:] == (self.params.H, 2)
-        out = np.empty((polys.shape[0], keys.shape[1], self.params.N), dtype=np.uint64)
-        self._ck(_lib.lib().mktfhe_gadget_product_batch(self._h, l, logB, _ptr(polys), _ptr(keys), keys.shape[1], _ptr(out),
-                                                        polys.shape[0]), "gadget_product")
+        out = np.empty((polys.shape[0], keys.shape[1], self.params.N), dtype=dt)
+        fn = _lib.lib().mktfhe_gadget_product_batch if dt == np.uint64 else _lib.lib().mktfhe_gadget_product32_batch
+        self._ck(fn(self._h, l, logB, _ptr(polys), _ptr(keys), keys.shape[1], _ptr(out), polys.shape[0]), "gadget_product")
         return out
 
     def fft(self, polys):
