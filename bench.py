@@ -270,7 +270,7 @@ ALSO = ("cggi", "kms8block", "kms32")
 # reference's flow: keys are built on the host).  "device": generated on every GPU from the seed (byte-identical, no PCIe / NVLink).
 # The headline keeps the host path; the 10.6 GB key set of KMS32party takes 15 s + 3 s that way and 2 s on the device.
 KEYGEN = {"kms2": "host", "kms8block": "host"}
-ALSO_STEPS, ALSO_WARMUP = 2, 1
+ALSO_STEPS, ALSO_WARMUP = 3, 3
 # Fraction of the sampled outputs that must decrypt correctly for the line to count (exit code 3 and "valid": false otherwise).
 # CCS16party / KMS32party sit at the decision margin in the reference algorithm itself: the CPU oracle fails 1.6 % of KMS32party
 # gates and ~5 % of CCS16party gates on the same inputs (tests/golden/failrate_*.npz).

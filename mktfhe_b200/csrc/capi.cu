@@ -79,6 +79,16 @@ int fail(mktfhe_ctx *c, int code, const std::string &msg) {
     } while (0)
 
 template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
+// temporary device buffer of a hook: released on every exit path (CK returns early on the first CUDA error)
+template <class T> struct DevTmp {
+    T *p = nullptr;
+    DevTmp() = default;
+    DevTmp(const DevTmp &) = delete;
+    DevTmp &operator=(const DevTmp &) = delete;
+    ~DevTmp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+    operator T *() const { return p; }
+};
 
 size_t per_gate_bytes(const mktfhe_ctx *c) {
     const mktfhe_params &p = c->p;
@@ -249,7 +259,7 @@ int run_blindrotate(mktfhe_ctx *ctx, const uint32_t *tilde, size_t gates, StageE
         if (fast2) rc = fast_phase1(ctx->fast, p, tilde, ctx->w_lev, gates, ctx->stream, &ctx->launches, ctx->err, true);
         else rc = run_phase1(ctx, tilde, ctx->w_lev, gates);
         if (rc) return rc;
-        if (ev) cudaEventRecord(ev->e[2], ctx->stream);
+        if (ev) CK(cudaEventRecord(ev->e[2], ctx->stream));
         if (fast2) rc = fast_phase2(ctx->fast, p, tilde, ctx->w_lev, (uint64_t *)ctx->w_acc, ctx->w_tx, ctx->w_ty, gates, ctx->stream, &ctx->launches, ctx->err);
         else rc = run_phase2(ctx, tilde, ctx->w_lev, (uint64_t *)ctx->w_acc, gates);
         if (rc) return rc;
@@ -259,7 +269,7 @@ int run_blindrotate(mktfhe_ctx *ctx, const uint32_t *tilde, size_t gates, StageE
         else
             rc = run_ccs(ctx, tilde, (uint32_t *)ctx->w_acc, gates);
         if (rc) return rc;
-        if (ev) cudaEventRecord(ev->e[2], ctx->stream);
+        if (ev) CK(cudaEventRecord(ev->e[2], ctx->stream));
     } else {
         if (ctx->mode == MKTFHE_MODE_FAST && fast32_supported(p)) {
             fast32::Args fa{};
@@ -270,7 +280,7 @@ int run_blindrotate(mktfhe_ctx *ctx, const uint32_t *tilde, size_t gates, StageE
             a.tilde = tilde; a.acc_io = ctx->w_acc; a.mode = RG_MODE_SK;
             if ((rc = run_rgsw(ctx, a, gates))) return rc;
         }
-        if (ev) cudaEventRecord(ev->e[2], ctx->stream);
+        if (ev) CK(cudaEventRecord(ev->e[2], ctx->stream));
     }
     return 0;
 }
@@ -523,9 +533,9 @@ __global__ void k_dfma_peak(double *out, int iters) {
 
 template <class T> int fft_hook(mktfhe_ctx *ctx, bool inverse, const void *in, void *out, size_t batch) {
     const int H = ctx->H, N = ctx->N;
-    T *d_poly = nullptr; cplx *d_spec = nullptr;
-    CK(cudaMalloc(&d_poly, batch * N * sizeof(T)));
-    CK(cudaMalloc(&d_spec, batch * H * sizeof(cplx)));
+    DevTmp<T> d_poly; DevTmp<cplx> d_spec;
+    CK(d_poly.alloc(batch * N * sizeof(T)));
+    CK(d_spec.alloc(batch * H * sizeof(cplx)));
     const int G = MK_THREADS / (H / 8);
     const size_t smem = (size_t)G * padded_len(H) * sizeof(cplx);
     const unsigned grid = (unsigned)((batch + G - 1) / G);
@@ -542,22 +552,20 @@ template <class T> int fft_hook(mktfhe_ctx *ctx, bool inverse, const void *in, v
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_poly); cudaFree(d_spec);
     return 0;
 }
 
 template <class T> int decomp_hook(mktfhe_ctx *ctx, int l, int logB, const void *polys, void *digits, size_t batch) {
     const int N = ctx->N;
     const size_t total = batch * N;
-    T *d_in = nullptr, *d_out = nullptr;
-    CK(cudaMalloc(&d_in, total * sizeof(T)));
-    CK(cudaMalloc(&d_out, total * l * sizeof(T)));
+    DevTmp<T> d_in, d_out;
+    CK(d_in.alloc(total * sizeof(T)));
+    CK(d_out.alloc(total * l * sizeof(T)));
     CK(cudaMemcpyAsync(d_in, polys, total * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     k_decomp_batch<T><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_in, d_out, N, l, logB, total);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(digits, d_out, total * l * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_in); cudaFree(d_out);
     return 0;
 }
 
@@ -912,13 +920,13 @@ static int run_pipeline(mktfhe_ctx *ctx, int gate_op, const uint32_t *in1, const
     int rc;
     StageEvents *ev = next_events(ctx);
     if (!ev) return fail(ctx, MKTFHE_ERR_CUDA, "cudaEventCreate failed");
-    cudaEventRecord(ev->e[0], ctx->stream);
+    CK(cudaEventRecord(ev->e[0], ctx->stream));
     if ((rc = run_prep(ctx, gate_op, in1, in2, nullptr, ctx->w_tilde, g, ops, idx1, idx2))) return rc;
-    cudaEventRecord(ev->e[1], ctx->stream);
+    CK(cudaEventRecord(ev->e[1], ctx->stream));
     if ((rc = run_blindrotate(ctx, ctx->w_tilde, g, ev))) return rc;
-    cudaEventRecord(ev->e[3], ctx->stream);
+    CK(cudaEventRecord(ev->e[3], ctx->stream));
     if ((rc = run_keyswitch(ctx, ctx->w_acc, out, g))) return rc;
-    cudaEventRecord(ev->e[4], ctx->stream);
+    CK(cudaEventRecord(ev->e[4], ctx->stream));
     return 0;
 }
 
@@ -1205,27 +1213,26 @@ static int step_impl(mktfhe_ctx *ctx, int party, int idx, const uint32_t *atilde
     const int lim = block_step ? ctx->p.d : ctx->p.n, per = block_step ? ctx->p.ell : 1;
     if (party < 0 || party >= ctx->nparties || idx < 0 || idx >= lim || !atilde || !acc_rows) return fail(ctx, MKTFHE_ERR_ARG, "bad argument");
     const size_t row_bytes = (size_t)2 * ctx->N * (ctx->bits / 8);
-    uint32_t *d_at = nullptr; void *d_rows = nullptr;
-    CK(cudaMalloc(&d_at, batch * 4 * per));
-    CK(cudaMalloc(&d_rows, batch * row_bytes));
+    DevTmp<uint32_t> d_at; DevTmp<unsigned char> d_rows;
+    CK(d_at.alloc(batch * 4 * per));
+    CK(d_rows.alloc(batch * row_bytes));
     CK(cudaMemcpyAsync(d_at, atilde, batch * 4 * per, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_rows, acc_rows, batch * row_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->mode == MKTFHE_MODE_FAST && fast_supported(ctx->p) && (block_step == ctx->block)) {
-        rc = fast_cmux_step(ctx->fast, ctx->p, party, idx, d_at, d_rows, batch, ctx->stream, &ctx->launches, ctx->err);
+        rc = fast_cmux_step(ctx->fast, ctx->p, party, idx, d_at, d_rows.p, batch, ctx->stream, &ctx->launches, ctx->err);
     } else if (ctx->mode == MKTFHE_MODE_FAST && fast32_supported(ctx->p) && (block_step == ctx->block)) {
         fast32::Args fa{};
-        fa.tilde = d_at; fa.acc_io = (uint32_t *)d_rows; fa.step_mode = block_step ? 2 : 1; fa.step_idx = idx; fa.units = batch;
+        fa.tilde = d_at; fa.acc_io = (uint32_t *)d_rows.p; fa.step_mode = block_step ? 2 : 1; fa.step_idx = idx; fa.units = batch;
         rc = fast32_launch(ctx->fast32, ctx->p, fa, ctx->stream, &ctx->launches, ctx->err);
     } else {
         RgswArgs a{};
-        a.tilde = d_at; a.acc_io = d_rows; a.mode = RG_MODE_STEP; a.step_party = party; a.step_idx = idx; a.step_block = block_step;
+        a.tilde = d_at; a.acc_io = d_rows.p; a.mode = RG_MODE_STEP; a.step_party = party; a.step_idx = idx; a.step_block = block_step;
         rc = run_rgsw(ctx, a, batch);
     }
     if (!rc) {
-        cudaMemcpyAsync(acc_rows, d_rows, batch * row_bytes, cudaMemcpyDeviceToHost, ctx->stream);
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, MKTFHE_ERR_CUDA, "cmux step failed");
+        CK(cudaMemcpyAsync(acc_rows, d_rows.p, batch * row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
     }
-    cudaFree(d_at); cudaFree(d_rows);
     return rc;
 }
 
@@ -1330,23 +1337,22 @@ int mktfhe_measure_dfma_peak(mktfhe_ctx *ctx, double *tflops_out) {
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     const int blocks = sms, threads = 512, iters = 1 << 15;
-    double *d = nullptr;
-    CK(cudaMalloc(&d, sizeof(double) * blocks * threads));
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    DevTmp<double> d;
+    CK(d.alloc(sizeof(double) * blocks * threads));
+    struct Ev { cudaEvent_t e = nullptr; ~Ev() { if (e) cudaEventDestroy(e); } } e0, e1;
+    CK(cudaEventCreate(&e0.e)); CK(cudaEventCreate(&e1.e));
     k_dfma_peak<<<blocks, threads, 0, ctx->stream>>>(d, iters);     // warm-up
     float best = 1e30f;
     for (int r = 0; r < 3; r++) {
-        CK(cudaEventRecord(e0, ctx->stream));
+        CK(cudaEventRecord(e0.e, ctx->stream));
         k_dfma_peak<<<blocks, threads, 0, ctx->stream>>>(d, iters);
-        CK(cudaEventRecord(e1, ctx->stream));
-        CK(cudaEventSynchronize(e1));
+        CK(cudaEventRecord(e1.e, ctx->stream));
+        CK(cudaEventSynchronize(e1.e));
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, e0, e1));
+        CK(cudaEventElapsedTime(&ms, e0.e, e1.e));
         if (ms < best) best = ms;
     }
     *tflops_out = (double)blocks * threads * iters * 16 * 2 / (best * 1e-3) / 1e12;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     return 0;
 }
 
