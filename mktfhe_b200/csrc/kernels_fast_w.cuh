@@ -500,14 +500,18 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
 #pragma unroll
                     for (int i = 0; i < 16; i++) v[0][i] = v[1][i] = 0x3ff00000u ^ (uint32_t)(i * t);
 #else
+#ifndef KO_MACNOLD
                     if (!first && NCH) tm_ld16(tmz, v[0]);
+#endif
 #endif
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
                         cplx kc[4], z[4];
 #pragma unroll
-#ifdef KO_KEYLDS
+#if defined(KO_KEYLDS)
                         for (int i = 0; i < 4; i++) kc[i] = c_tw1w[(4 * c + i) & 31];
+#elif defined(KO_KEYHALF)                       // half of the key reads (every value used twice)
+                        for (int i = 0; i < 4; i++) kc[i] = kp[(4 * c + (i & 1)) * 32];
 #else
                         for (int i = 0; i < 4; i++) kc[i] = kp[(4 * c + i) * 32];
 #endif
@@ -515,17 +519,29 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
 #pragma unroll
                             for (int i = 0; i < 4; i++) z[i] = cmul_f(x[4 * c + i], kc[i]);
                         } else {
-#ifndef KO_MACTM
+#if defined(KO_MACNOLD)                         // no TMEM loads in the sweep (stores stay)
+                            if (c == 0) {
+#pragma unroll
+                                for (int i = 0; i < 16; i++) v[0][i] = v[1][i] = 0x3ff00000u ^ (uint32_t)(i * t);
+                            }
+#elif !defined(KO_MACTM)
                             tm_wait_ld();
                             tm_pin16(v[c & 1]);
                             if (c < 7) tm_ld16(tmz + 16 * (c + 1), v[(c + 1) & 1]);
 #endif
 #pragma unroll
+#ifdef KO_MACNOFMA                              // loads and stores stay, no arithmetic
+                            for (int i = 0; i < 4; i++) z[i] = unpack_c(v[c & 1], i);
+#else
                             for (int i = 0; i < 4; i++) z[i] = cmac_f(unpack_c(v[c & 1], i), x[4 * c + i], kc[i]);
+#endif
                         }
 #ifdef KO_MACTM
 #pragma unroll
                         for (int i = 0; i < 4; i++) { x[4 * c + i].x += z[i].x * 1e-300; x[4 * c + i].y += z[i].y * 1e-300; }   // keep the arithmetic alive
+#elif defined(KO_MACNOST)                       // no TMEM stores in the sweep (loads and arithmetic stay: a store that never happens keeps them alive)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) if (z[i].x == 1.2345e-300) a.lev_out[i] = z[i];
 #else
                         tm_st_c4(tmz + 16 * c, z);
 #endif
