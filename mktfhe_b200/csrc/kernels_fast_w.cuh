@@ -36,6 +36,11 @@ constexpr int WU = 4;                       // units per CTA = TMEM lane quadran
 constexpr int NCW = 2 * WU;                 // consumer warps
 constexpr int CTA_W = NCW * 32 + 128;       // + producer warpgroup (setmaxnreg works on warpgroups)
 constexpr int XBW = H + 32;                 // exchange buffer: element n at n + (n >> 5)
+
+// ---- build switches (production values are the defaults; set with MKTFHE_NVCC_EXTRA, see mktfhe_b200/build.py) --------------------
+//   W_INV_DIT, W_RING, W_FIRST_STORE, W_CREGS, W_DECOMP_I2F   measured alternatives, each described where it is used
+//   KO_*                                                        knock-out TIMING builds: parts of the work removed, results wrong by
+//                                                               construction (profiles/README_r2.md lists what each one really removes)
 // W_INV_DIT: the inverse transform as a plain decimation-in-time network + untwist (tools/models/ifft_dit_model.py) instead of the
 // forward product tree walked backwards: multiply-then-add butterflies (6 FMA-pipe instructions against 8), twiddles 1 and i in
 // the first two stages, one complex multiplication per point for the untwist: 31.9k FP64 instructions per transform instead of
@@ -51,10 +56,10 @@ constexpr int XBW = H + 32;                 // exchange buffer: element n at n +
 #endif
 constexpr int RINGW = W_RING;               // key tiles (16 KiB polynomials) in flight
 #ifndef W_FIRST_STORE
-#define W_FIRST_STORE 0
+#define W_FIRST_STORE 0                     // see the sweep loop
 #endif
 #ifndef W_CREGS
-#define W_CREGS 232
+#define W_CREGS 232                         // consumer registers after setmaxnreg; 240 is the most the launch allocation allows
 #endif
 #define W_STR2(x) #x
 #define W_STR(x) W_STR2(x)
