@@ -24,7 +24,7 @@ CUDA_LIB = os.environ.get("MKTFHE_CUDA_LIB") or os.path.join(LIBDIR, "libmktfhe_
 
 HOST_SRCS = ["host_keygen.cpp"]
 CUDA_SRCS = ["capi.cu"]
-CUDA_DEPS = ["common.cuh", "fft_strict.cuh", "kernels_strict.cuh", "kernels_fast.cuh", "kernels_fast_w.cuh", "kernels_fast32.cuh", "keyswitch.cuh", "keygen.cuh"]
+CUDA_DEPS = ["common.cuh", "fft_strict.cuh", "kernels_strict.cuh", "kernels_fast.cuh", "kernels_fast_w.cuh", "kernels_fast32.cuh", "kernels_fast32_w.cuh", "keyswitch.cuh", "keygen.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

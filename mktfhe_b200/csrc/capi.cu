@@ -16,6 +16,7 @@
 #include "keyswitch.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_fast32.cuh"
+#include "kernels_fast32_w.cuh"
 #include "keygen.cuh"
 
 namespace {
@@ -43,6 +44,7 @@ struct mktfhe_ctx {
     bool finalized = false;
     FastKeys fast;
     FastKeys32 fast32;
+    FastKeys32W fast32w;           // CGGI, half-warp transform (kernels_fast32_w.cuh)
     FastCcsKeys fastccs;
     // workspace for `cap` gates
     size_t cap = 0;
@@ -250,6 +252,18 @@ int run_keyswitch(mktfhe_ctx *ctx, const void *acc, uint32_t *out, size_t gates)
 }
 
 // blind rotation of `gates` ciphertexts whose tilde is in w_tilde -> w_acc
+// N = 1024 single-key schemes in FAST mode: CGGI runs the half-warp-transform kernel (kernels_fast32_w.cuh), LMSS the 64-thread
+// kernel with the TMA key ring (kernels_fast32.cuh).  MKTFHE_FAST32_KERNEL = tmem | tma forces the 64-thread kernels for CGGI too.
+int launch_fast32(mktfhe_ctx *ctx, const fast32::Args &fa) {
+    static const bool force64 = []() { const char *e = getenv("MKTFHE_FAST32_KERNEL"); return e && (std::string(e) == "tmem" || std::string(e) == "tma"); }();
+    if (ctx->p.scheme == MKTFHE_CGGI && ctx->fast32w.built && !force64) {
+        fastw32::Args wa{};
+        wa.tilde = fa.tilde; wa.acc_io = fa.acc_io; wa.step_mode = fa.step_mode; wa.step_idx = fa.step_idx; wa.units = fa.units;
+        return fast32w_launch(ctx->fast32w, ctx->fast32.emono, ctx->p, wa, ctx->stream, &ctx->launches, ctx->err);
+    }
+    return fast32_launch(ctx->fast32, ctx->p, fa, ctx->stream, &ctx->launches, ctx->err);
+}
+
 int run_blindrotate(mktfhe_ctx *ctx, const uint32_t *tilde, size_t gates, StageEvents *ev) {
     const mktfhe_params &p = ctx->p;
     int rc;
@@ -274,7 +288,7 @@ int run_blindrotate(mktfhe_ctx *ctx, const uint32_t *tilde, size_t gates, StageE
         if (ctx->mode == MKTFHE_MODE_FAST && fast32_supported(p)) {
             fast32::Args fa{};
             fa.tilde = tilde; fa.acc_io = (uint32_t *)ctx->w_acc; fa.step_mode = 0; fa.units = gates;
-            if ((rc = fast32_launch(ctx->fast32, p, fa, ctx->stream, &ctx->launches, ctx->err))) return rc;
+            if ((rc = launch_fast32(ctx, fa))) return rc;
         } else {
             RgswArgs a{};
             a.tilde = tilde; a.acc_io = ctx->w_acc; a.mode = RG_MODE_SK;
@@ -741,6 +755,7 @@ void mktfhe_ctx_destroy(mktfhe_ctx *ctx) {
     free_wires(ctx);
     fast_free(ctx->fast);
     fast32_free(ctx->fast32);
+    fast32w_free(ctx->fast32w);
     fastccs_free(ctx->fastccs);
     for (auto &q : ctx->brk) dfree(q);
     for (auto &q : ctx->rlk) dfree(q);
@@ -895,6 +910,7 @@ int mktfhe_finalize_keys(mktfhe_ctx *ctx) {
     CK(cudaGetLastError());
     if (fast_supported(ctx->p) && (rc = fast_build(ctx->fast, ctx->p, ctx->brk, ctx->rlk, ctx->pubb, ctx->crs, ctx->stream, ctx->err))) return rc;
     if (fast32_supported(ctx->p) && (rc = fast32_build(ctx->fast32, ctx->p, ctx->brk[0], ctx->stream, ctx->err))) return rc;
+    if (fast32_supported(ctx->p) && ctx->p.scheme == MKTFHE_CGGI && (rc = fast32w_build(ctx->fast32w, ctx->p, ctx->brk[0], ctx->stream, ctx->err))) return rc;
     if (fastccs_supported(ctx->p)) {
         if ((rc = fast32_build(ctx->fast32, ctx->p, nullptr, ctx->stream, ctx->err))) return rc;      // transform tables only
         if ((rc = fastccs_build(ctx->fastccs, ctx->p, ctx->brk, ctx->pubb, ctx->crs, ctx->stream, ctx->err))) return rc;
@@ -1223,7 +1239,7 @@ static int step_impl(mktfhe_ctx *ctx, int party, int idx, const uint32_t *atilde
     } else if (ctx->mode == MKTFHE_MODE_FAST && fast32_supported(ctx->p) && (block_step == ctx->block)) {
         fast32::Args fa{};
         fa.tilde = d_at; fa.acc_io = (uint32_t *)d_rows.p; fa.step_mode = block_step ? 2 : 1; fa.step_idx = idx; fa.units = batch;
-        rc = fast32_launch(ctx->fast32, ctx->p, fa, ctx->stream, &ctx->launches, ctx->err);
+        rc = launch_fast32(ctx, fa);
     } else {
         RgswArgs a{};
         a.tilde = d_at; a.acc_io = d_rows.p; a.mode = RG_MODE_STEP; a.step_party = party; a.step_idx = idx; a.step_block = block_step;
