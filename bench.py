@@ -420,7 +420,7 @@ def run_workload(ctx, workload, batch, steps, warmup, headline, want_cpu_baselin
         dom_ms = stage_ms["phase1"]
         peak = scheme.dfma_peak_tflops()
         ach = alg["phase1"] * batch / (dom_ms * 1e-3) / 1e3 if dom_ms > 0 else 0.0
-        line["roofline"] = {"bound": "fp64", "kernel": "blind rotation (FP64 transforms + pointwise MAC): fastw::k_phase1_w / fast::k_phase1_tma<3> / fast32::k_rgsw_tm / k_ccs_fast",
+        line["roofline"] = {"bound": "fp64", "kernel": "blind rotation (FP64 transforms + pointwise MAC): fastw::k_phase1_w / fast::k_phase1_tma<3> / fastw32::k_cggi_w / fast32::k_rgsw_tma<3> / k_ccs_fast",
                             "achieved": ach, "peak": peak,
                             "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": traffic.get(workload, {}).get("phase1"),
                             "traffic_source": traffic_note,

@@ -14,8 +14,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SOURCES = ["mktfhe_b200/csrc/kernels_fast.cuh", "mktfhe_b200/csrc/kernels_fast_w.cuh", "mktfhe_b200/csrc/kernels_fast32.cuh",
+           "mktfhe_b200/csrc/kernels_fast32_w.cuh",
            "mktfhe_b200/csrc/keyswitch.cuh", "mktfhe_b200/csrc/capi.cu"]
-CLASSES = (("phase1", ("k_phase1", "k_rgsw_tm", "k_ccs_fast", "k_rgsw_blindrotate", "k_ccs_blindrotate")),
+CLASSES = (("phase1", ("k_phase1", "k_rgsw_tm", "k_cggi_w", "k_ccs_fast", "k_rgsw_blindrotate", "k_ccs_blindrotate")),
            ("phase2", ("k_phase2", "k_kms_phase2")), ("keyswitch", ("k_keyswitch",)))
 
 
