@@ -39,7 +39,10 @@ constexpr int GATES_CTA = 2 * WQ;
 constexpr int NCW = 2 * WQ;                  // consumer warps
 constexpr int CTA_W = NCW * 32 + 128;        // + producer warpgroup (setmaxnreg works on warpgroups)
 constexpr int XBH = H + 16;                  // exchange buffer of a half-warp: position q at q + (q >> 5)
-constexpr int RINGW = 8;                     // key tiles (8 KiB polynomials) in flight
+#ifndef W32_RING
+#define W32_RING 6
+#endif
+constexpr int RINGW = W32_RING;              // key tiles (8 KiB polynomials) in flight; 4, 6, 11 measured equal (41.6 ms), 8 one percent slower
 constexpr int W_LAUNCH_REGS = 168, W_CONSUMER_REGS = 232, W_PRODUCER_REGS = 24;
 static_assert(NCW * W_CONSUMER_REGS + 4 * W_PRODUCER_REGS <= (CTA_W / 32) * W_LAUNCH_REGS, "setmaxnreg over-subscription");
 constexpr size_t SMEM_BYTES_W = ((size_t)NCW * 2 * XBH + 256 + (size_t)RINGW * H) * 16 + (2 * RINGW + 4 * WQ) * 8 + 16;
