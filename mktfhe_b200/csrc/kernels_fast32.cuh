@@ -653,7 +653,8 @@ static inline int fast32_launch(FastKeys32 &f, const mktfhe_params &p, fast32::A
     // Keys by per-thread loads (k_rgsw_tm) or through a TMA ring shared by the CTA's eight gates (k_rgsw_tma).  Measured on B200,
     // 4096 gates: LMSS 78.7 ms -> 31.6 ms with the ring (its 48 dependent key loads per digit leave the critical path), CGGI
     // 47.1 ms -> 55.1 ms (one key tile per digit: the ring's mbarrier round trips cost more than the loads they replace).
-    // Default: ring for LMSS, per-thread loads for CGGI; MKTFHE_FAST32_KERNEL = tmem | tma forces one for both (A/B runs).
+    // Default here: ring for LMSS, per-thread loads for CGGI; MKTFHE_FAST32_KERNEL = tmem | tma forces one for both (A/B runs).
+    // (CGGI gate batches do not come here by default any more: capi.cu sends them to fastw32::k_cggi_w, kernels_fast32_w.cuh.)
     static const int force = []() { const char *e = getenv("MKTFHE_FAST32_KERNEL"); return !e ? 0 : std::string(e) == "tma" ? 1 : std::string(e) == "tmem" ? 2 : 0; }();
     const bool blk = p.scheme == MKTFHE_LMSS && !(a.step_mode == 1);
     const bool tma = force == 1 || (force == 0 && blk);
