@@ -45,6 +45,7 @@ constexpr int XBH = H + 16;                  // exchange buffer of a half-warp: 
 constexpr int RINGW = W32_RING;              // key tiles (8 KiB polynomials) in flight; 4, 6, 11 measured equal (41.6 ms), 8 one percent slower
 constexpr int W_LAUNCH_REGS = 168, W_CONSUMER_REGS = 232, W_PRODUCER_REGS = 24;
 static_assert(NCW * W_CONSUMER_REGS + 4 * W_PRODUCER_REGS <= (CTA_W / 32) * W_LAUNCH_REGS, "setmaxnreg over-subscription");
+static_assert(RINGW % 2 == 0, "ring depth must be even: a slot must always serve the same kind of warp (see kernels_fast_w.cuh)");
 constexpr size_t SMEM_BYTES_W = ((size_t)NCW * 2 * XBH + 256 + (size_t)RINGW * H) * 16 + (2 * RINGW + 4 * WQ) * 8 + 16;
 static_assert(SMEM_BYTES_W <= 232448, "shared memory budget");
 

@@ -52,9 +52,15 @@ constexpr int XBW = H + 32;                 // exchange buffer: element n at n +
 #define W_INV_DIT 0
 #endif
 #ifndef W_RING
-#define W_RING (W_INV_DIT ? 4 : 5)
+#define W_RING 4
 #endif
 constexpr int RINGW = W_RING;               // key tiles (16 KiB polynomials) in flight
+// The ring depth must be EVEN.  Tiles alternate between the A warps and the B warps, so with an odd depth a slot alternates too and a
+// warp sees only every second phase of its slot's `full` barrier; a parity wait cannot tell "my phase" from "two phases earlier".  A
+// warp that runs ahead (dead units of a small batch, a skipped step) then takes the completion of the tile BEFORE the other warps'
+// tile for its own when bulk copies complete out of order, releases the slot twice, and the CTA deadlocks: seen at KMS32party with
+// one gate per call (one run in three) with the five-tile ring; with an even depth every slot belongs to one kind of warp.
+static_assert(RINGW % 2 == 0, "ring depth must be even: a slot must always serve the same kind of warp");
 #ifndef W_FIRST_STORE
 #define W_FIRST_STORE 0                     // see the sweep loop
 #endif

@@ -168,3 +168,22 @@ def test_failure_rate_matches_oracle(gpu_schemes, name):
     pbar = max((fail_f + fail_o) / (2.0 * count), 1.0 / count)
     assert abs(fail_f - fail_o) <= 4.0 * np.sqrt(2.0 * count * pbar * (1 - pbar)) + 1
     assert 0.9 < sd_f / sd_o < 1.1
+
+
+@pytest.mark.timeout(300)
+def test_single_gate_calls_at_kms32_do_not_deadlock(gpu_schemes):
+    """Regression: with one gate per call most units of a phase-1 CTA are dead and race ahead through the key ring.  With an odd
+    ring depth a slot alternated between the two kinds of consumer warps and a warp that ran ahead could take the completion of an
+    older tile for its own (bulk copies of a 7 GB key set complete out of order): one KMS32party call in three hung.  The ring
+    depth is even now (csrc/kernels_fast_w.cuh); every repetition must return, decrypt and agree with the first."""
+    ks = keyset("KMS32party")
+    s = gpu_schemes("KMS32party")
+    s.set_mode(MODE_FAST)
+    b1, c1 = fresh_inputs(ks, 1, seed=901)
+    b2, c2 = fresh_inputs(ks, 1, seed=902)
+    first = s.gate(0, c1, c2)
+    for _ in range(15):
+        assert np.array_equal(s.gate(0, c1, c2), first)
+    lev = s.phase1(s.gate_linear(0, c1, c2))
+    for _ in range(15):
+        assert np.array_equal(s.phase1(s.gate_linear(0, c1, c2)), lev)
