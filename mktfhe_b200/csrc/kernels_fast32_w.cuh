@@ -43,7 +43,10 @@ constexpr int XBH = H + 16;                  // exchange buffer of a half-warp: 
 #define W32_RING 6
 #endif
 constexpr int RINGW = W32_RING;              // key tiles (8 KiB polynomials) in flight; 4, 6, 11 measured equal (41.6 ms), 8 one percent slower
-constexpr int W_LAUNCH_REGS = 168, W_CONSUMER_REGS = 232, W_PRODUCER_REGS = 24;
+#ifndef W32_CREGS
+#define W32_CREGS 232
+#endif
+constexpr int W_LAUNCH_REGS = 168, W_CONSUMER_REGS = W32_CREGS, W_PRODUCER_REGS = 24;
 static_assert(NCW * W_CONSUMER_REGS + 4 * W_PRODUCER_REGS <= (CTA_W / 32) * W_LAUNCH_REGS, "setmaxnreg over-subscription");
 static_assert(RINGW % 2 == 0, "ring depth must be even: a slot must always serve the same kind of warp (see kernels_fast_w.cuh)");
 constexpr size_t SMEM_BYTES_W = ((size_t)NCW * 2 * XBH + 256 + (size_t)RINGW * H) * 16 + (2 * RINGW + 4 * WQ) * 8 + 16;
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_cggi_w(const Args a) {
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " W_STR(W32_CREGS) ";");
         // ---- consumers: quadrant q = two gates (half-warps), role w (0 = A: the .b halves, 1 = B: the .a halves)
         const int q = warp & 3, w = warp >> 2;
         const uint32_t tk = smem_u32(tokens + 4 * q), full_s = smem_u32(full), empty_s = smem_u32(empty);

@@ -51,22 +51,24 @@ constexpr int XBW = H + 32;                 // exchange buffer: element n at n +
 #ifndef W_INV_DIT
 #define W_INV_DIT 0
 #endif
-#ifndef W_RING
-#define W_RING 4
+// Key tiles (16 KiB polynomials) in flight: TWO rings, one per kind of consumer warp (tiles alternate A, B, A, B).  A slot must always
+// serve the same kind of warp: in one ring of odd depth a slot alternated between the kinds, a warp saw only every second phase of
+// its slot's `full` barrier, and a parity wait cannot tell "my phase" from "two phases earlier" -- a warp that ran ahead (dead units of
+// a small batch, a skipped step) took the completion of the tile BEFORE the other kind's tile for its own when bulk copies completed
+// out of order, released the slot twice, and the CTA deadlocked (KMS32party with one gate per call: one run in three).
+#ifndef W_RING_A
+#define W_RING_A 3
 #endif
-constexpr int RINGW = W_RING;               // key tiles (16 KiB polynomials) in flight
-// The ring depth must be EVEN.  Tiles alternate between the A warps and the B warps, so with an odd depth a slot alternates too and a
-// warp sees only every second phase of its slot's `full` barrier; a parity wait cannot tell "my phase" from "two phases earlier".  A
-// warp that runs ahead (dead units of a small batch, a skipped step) then takes the completion of the tile BEFORE the other warps'
-// tile for its own when bulk copies complete out of order, releases the slot twice, and the CTA deadlocks: seen at KMS32party with
-// one gate per call (one run in three) with the five-tile ring; with an even depth every slot belongs to one kind of warp.
-static_assert(RINGW % 2 == 0, "ring depth must be even: a slot must always serve the same kind of warp");
+#ifndef W_RING_B
+#define W_RING_B (W_INV_DIT ? 1 : 2)
+#endif
+constexpr int RING_A = W_RING_A, RING_B = W_RING_B, RINGW = RING_A + RING_B;
 #ifndef W_FIRST_STORE
 #define W_FIRST_STORE 0                     // see the sweep loop
 #endif
 #ifndef W_CREGS
-#define W_CREGS 232                         // consumer registers after setmaxnreg; 240 is the most the launch allocation allows
-#endif
+#define W_CREGS 240                         // consumer registers after setmaxnreg: all the launch allocation allows (8 x 240 + 4 x 24 = 12 x 168);
+#endif                                      // 232 left 24 B of spills after the key ring was split in two: 211.9 against 205.0 ms at KMS2party
 #define W_STR2(x) #x
 #define W_STR(x) W_STR2(x)
 constexpr int W_LAUNCH_REGS = 168, W_CONSUMER_REGS = W_CREGS, W_PRODUCER_REGS = 24;
@@ -306,9 +308,9 @@ __device__ __forceinline__ void token_pass(uint32_t bar, int t) {     // all lan
 #endif
 }
 // ring position of a consumer warp: tile -> (slot, phase parity), advanced without divisions
-struct RingPos {
+struct RingPos {                             // role w walks the slots [0, RING_A) (A) or [RING_A, RINGW) (B) of its own ring
     uint32_t slot, par;
-    __device__ __forceinline__ void advance(uint32_t by) { slot += by; if (slot >= RINGW) { slot -= RINGW; par ^= 1; } }
+    __device__ __forceinline__ void advance(int w) { if (++slot == (w ? (uint32_t)RINGW : (uint32_t)RING_A)) { slot = w ? (uint32_t)RING_A : 0u; par ^= 1; } }
 };
 
 __device__ __forceinline__ cplx unpack_c(const uint32_t (&v)[16], int i) {
@@ -362,14 +364,19 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
         // ---- producer: 16 KiB polynomials in thread order [e][t], in consumption order: per step and j < l the four tiles
         //      A_j.b = (digit j, .b), B_j.a = (digit l + j, .a), A_j.a = (digit j, .a), B_j.b = (digit l + j, .b)
         if (tid == NCW * 32) {
-            uint32_t slot = 0, par = 1, step = 0, j = 0, r = 0;         // par: parity of the PREVIOUS phase of empty[slot]
+            uint32_t step = 0, j = 0, r = 0;
+            // per ring: next slot, parity of the PREVIOUS phase of that slot's empty barrier; the first lap needs no wait
+            uint32_t sa = 0, pa = 1, sb = RING_A, pb = 1;
             for (uint32_t n = 0; n < ntiles; n++) {
-                if (n >= RINGW) mb_wait_sleep(&empty[slot], par);
+                const bool kb = r & 1;                                 // tile for the B warps
+                const uint32_t slot = kb ? sb : sa;
+                if (n >= 2 * (kb ? RING_B : RING_A)) mb_wait_sleep(&empty[slot], kb ? pb : pa);
                 const uint32_t dg = (r & 1) ? (uint32_t)l + j : j, comp = (r == 1 || r == 2) ? 1u : 0u;
                 const int idx = a.step_mode ? a.step_idx : (int)step;
                 mb_expect_tx(&full[slot], H * 16);
                 bulk_g2s(ring + (size_t)slot * H, brk + (size_t)idx * per_idx + (size_t)(dg * 2 + comp) * H, H * 16, &full[slot]);
-                if (++slot == RINGW) { slot = 0; par ^= 1; }
+                if (kb) { if (++sb == RINGW) { sb = RING_A; pb ^= 1; } }
+                else { if (++sa == RING_A) { sa = 0; pa ^= 1; } }
                 if (++r == 4) { r = 0; if (++j == (uint32_t)l) { j = 0; step++; } }
             }
         }
@@ -439,8 +446,8 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
         const int hB = 1 << (logB - 1);
         const uint32_t *at_src = a.step_mode ? a.tilde + up : a.tilde + (size_t)gate * a.lwe_words + 1 + (size_t)party * a.n;
         const int brv5t = (int)(__brev((unsigned)t) >> 27);
-        // this warp consumes every second tile of the producer's sequence, starting at tile w
-        RingPos rp{(uint32_t)w, 0u};
+        // this warp consumes every second tile of the producer's sequence, starting at tile w, from its own ring
+        RingPos rp{w == 0 ? 0u : (uint32_t)RING_A, 0u};
 
         for (int step = 0; step < nsteps; step++) {
             const uint32_t at = live ? at_src[a.step_mode ? 0 : step] : 0u;
@@ -449,7 +456,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                     mbs_wait<SUSPEND>(full_s + 8u * rp.slot, rp.par);
                     __syncwarp();
                     if (t == 0) mbs_arrive(empty_s + 8u * rp.slot);
-                    rp.advance(2);
+                    rp.advance(w);
                 }
                 continue;
             }
@@ -561,7 +568,7 @@ __global__ void __launch_bounds__(CTA_W, 1) k_phase1_w(const fast::Args a) {
                     tm_fence_before();
                     token_pass(ps == 0 ? pass_own : pass_oth, t);      // also orders every lane's key reads before the release below
                     if (t == 0) mbs_arrive(empty_s + 8u * rp.slot);     // this key tile is done
-                    rp.advance(2);
+                    rp.advance(w);
                 }
             }
             wait_own.wait();                                        // the other warp's last addition into my sum
