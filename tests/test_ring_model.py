@@ -57,3 +57,28 @@ def test_even_shared_ring_and_other_splits_are_safe():
     # every odd shared depth has the defect, not just five
     for d in (3, 7):
         assert m.check(("one", d), units=2, ntiles=4 * d, coupled=False)[0] != "ok", d
+
+
+def _token_model():
+    spec = importlib.util.spec_from_file_location("token_model", os.path.join(ROOT, "tools", "models", "token_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("l", [1, 2, 3, 5, 6])
+def test_token_order_of_the_two_warps(l):
+    """Four tokens per unit: exclusive sweeps, fixed order of the additions, complete sums at the step end, no lapped token, no
+    deadlock -- for every gadget length of params.jl's KMS sets (l_gsw = 3, 5, 6) and with skipped steps (a~ = 0)."""
+    m = _token_model()
+    assert m.check(l, (False, False, False)) == "ok"
+    assert m.check(l, (False, True, False, True, False)) == "ok"
+
+
+def test_token_model_finds_every_missing_wait():
+    m = _token_model()
+    for w in range(2):
+        nwait = sum(1 for op in m.program(w, 3, (False, False)) if op[0] == m.WAIT)
+        assert nwait == 12
+        for k in range(nwait):
+            assert m.check(3, (False, False), drop_wait=(w, k)) != "ok", (w, k)
