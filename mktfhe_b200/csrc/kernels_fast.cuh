@@ -1603,6 +1603,9 @@ static inline bool fast_variant_tma() { return fast_variant() == "tma" || fast_v
 static inline bool fast_use_w(const mktfhe_params &p) { return fast_variant() == "w32" && p.scheme == MKTFHE_KMS; }
 
 static inline bool fast_supported(const mktfhe_params &p) {
+    // the 64-bit kernels form the rounding constant 1 << (64 - l*logB - 1): a gadget that fills the whole word (no named set of
+    // params.jl does; the tightest is 22 spare bits) runs the STRICT kernels instead
+    if (p.l_gsw * p.logB_gsw >= 64 || p.l_lev * p.logB_lev >= 64 || p.l_uni * p.logB_uni >= 64) return false;
     return p.N == 2048 && (p.scheme == MKTFHE_KMS || (p.scheme == MKTFHE_KMS_BLOCK && p.ell == 3));
 }
 

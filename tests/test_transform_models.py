@@ -58,3 +58,44 @@ def test_monomial_closed_form_per_thread_and_register_slot(name, tbits):
                 z = m1 * np.exp(-1j * np.pi * ((a * m.brv(e, 5)) % 32) / 16) - 1
                 worst = max(worst, abs(z - mono[32 * t + e]))
         assert worst < 1e-12, (name, a, worst)
+
+
+def _gadgets():
+    """Every (word width, l, logB) a FAST kernel decomposes with: the three gadgets of each named parameter set (params.jl)."""
+    from mktfhe_b200 import params as P
+    seen = set()
+    for p in P.ALL.values():
+        w = 64 if p.N == 2048 else 32
+        for l, b in ((p.l_gsw, p.logB_gsw), (p.l_lev, p.logB_lev), (p.l_uni, p.logB_uni)):
+            if l:
+                seen.add((w, l, b))
+    return sorted(seen)
+
+
+@pytest.mark.parametrize("w,l,logB", _gadgets())
+def test_one_add_field_extraction_equals_the_reference_digits(w, l, logB):
+    """FAST decomposition (kernels_fast*.cuh): the accumulator is kept with ONE constant added -- half an ulp of the kept precision
+    (divbits rounding, arithmetic.jl:23-27) plus B/2 at every digit position -- after which digit j is the plain bit field
+    ((x + cadd) >> shift_j) & (B - 1), minus B/2.  Must equal the reference's rounding + carry chain (gsw.jl:86-96) digit for digit,
+    including at the wrap-around values, for every gadget of params.jl."""
+    from oracle import oracle as O
+    dt = np.uint64 if w == 64 else np.uint32
+    rng = np.random.default_rng(w * 1000 + l * 37 + logB)
+    x = rng.integers(0, 2 ** w, size=4096, dtype=dt)
+    bit = w - l * logB
+    edges = [0, 1, 2 ** w - 1, 2 ** (w - 1), 2 ** (w - 1) - 1, 2 ** (w - 1) + 1]
+    for j in range(l + 1):                       # values sitting exactly on and next to every rounding / carry boundary
+        pos = bit + j * logB - 1
+        if pos >= 0:
+            edges += [(1 << pos) % 2 ** w, ((1 << pos) - 1) % 2 ** w, (2 ** w - (1 << pos)) % 2 ** w, (2 ** w - (1 << pos) - 1) % 2 ** w]
+    x[:len(edges)] = np.array(edges, dtype=object).astype(dt)
+    ref = O.decomp(x, l, logB)                   # [l][n], two's complement in the word type, digit 0 most significant
+    cadd = (1 << (bit - 1)) if bit > 0 else 0
+    for j in range(l):
+        cadd += 1 << (bit + j * logB + logB - 1)
+    mask, half = (1 << logB) - 1, 1 << (logB - 1)
+    for j in range(l):
+        sh = bit + (l - 1 - j) * logB
+        got = [(((int(v) + cadd) % 2 ** w) >> sh & mask) - half for v in x]
+        want = ref[j].astype(np.int64) if w == 64 else ref[j].astype(np.int32).astype(np.int64)
+        assert got == [int(v) for v in want], (w, l, logB, j)
