@@ -20,6 +20,8 @@ consumed (no deadlock).
 
 Ring layouts:  ("one", D)      one ring of D slots shared by both kinds, tile n in slot n mod D  (round-2 build before the fix: D = 5)
                ("two", RA, RB) one ring per kind (shipped: 3 + 2)
+               ("all", D)      one ring of D slots, EVERY consumer reads EVERY tile (fast::k_phase1_tma, fast32::k_rgsw_tma, the
+                               tiled key switch): every waiter sees every phase, so any depth works
 
     python tools/models/key_ring_model.py          # prints the verdict for the layouts discussed in profiles/README_r2.md
 """
@@ -30,7 +32,7 @@ from collections import deque
 
 def _place(layout, n):
     """tile n -> (slot, lap of that slot's ring, ring depth).  Kind = n & 1."""
-    if layout[0] == "one":
+    if layout[0] in ("one", "all"):
         d = layout[1]
         return n % d, n // d, d
     ra, rb = layout[1], layout[2]
@@ -41,12 +43,12 @@ def _place(layout, n):
 
 
 def _nslots(layout):
-    return layout[1] if layout[0] == "one" else layout[1] + layout[2]
+    return layout[1] if layout[0] in ("one", "all") else layout[1] + layout[2]
 
 
 def _first_lap(layout, n):
     """The producer's `if (n >= ...)` test: no wait during the first lap of the ring the tile belongs to."""
-    if layout[0] == "one":
+    if layout[0] in ("one", "all"):
         return n < layout[1]
     return (n >> 1) < (layout[2] if n & 1 else layout[1])
 
@@ -54,10 +56,13 @@ def _first_lap(layout, n):
 def check(layout, units=2, ntiles=24, coupled=False, max_states=4_000_000):
     """Returns ("ok", states) or (reason, trace_length)."""
     ns = _nslots(layout)
+    every = layout[0] == "all"                 # one kind of consumer that reads every tile
+    nk = 1 if every else 2
+    tile = (lambda k, i: i) if every else (lambda k, i: 2 * i + k)
     # state = (prod_n, cons, slots); cons[kind * units + u] = (own index i, reading 0/1)
     # slots[s] = (full_done, empty_done, empty_cnt, content, inflight)   content: tile id, -1 nothing, -2 being written
-    init = (0, tuple((0, 0) for _ in range(2 * units)), tuple((0, 0, 0, -1, -1) for _ in range(ns)))
-    per_kind = [(ntiles + 1) // 2, ntiles // 2]
+    init = (0, tuple((0, 0) for _ in range(nk * units)), tuple((0, 0, 0, -1, -1) for _ in range(ns)))
+    per_kind = [ntiles] if every else [(ntiles + 1) // 2, ntiles // 2]
     seen = {init}
     todo = deque([init])
     while todo:
@@ -75,10 +80,10 @@ def check(layout, units=2, ntiles=24, coupled=False, max_states=4_000_000):
             if ok:
                 if infl != -1:
                     return "two copies in flight to one slot", len(seen)
-                for k in range(2):
+                for k in range(nk):
                     for u in range(units):
                         i, rd = cons[k * units + u]
-                        if rd and _place(layout, 2 * i + k)[0] == s:
+                        if rd and _place(layout, tile(k, i))[0] == s:
                             return "copy issued into a slot that is being read", len(seen)
                 ns_ = list(slots)
                 ns_[s] = (fd, ed, ec, -2, prod_n)
@@ -91,16 +96,16 @@ def check(layout, units=2, ntiles=24, coupled=False, max_states=4_000_000):
                 ns_[s] = (fd + 1, ed, ec, infl, -1)
                 succ.append((prod_n, cons, tuple(ns_)))
         # ---- consumers
-        for k in range(2):
+        for k in range(nk):
             for u in range(units):
                 i, rd = cons[k * units + u]
                 if i >= per_kind[k]:
                     continue
-                n = 2 * i + k
+                n = tile(k, i)
                 s, lap, _ = _place(layout, n)
                 fd, ed, ec, content, infl = slots[s]
                 if not rd:
-                    if coupled and cons[(1 - k) * units + u][0] < min(i, per_kind[1 - k]):
+                    if coupled and not every and cons[(1 - k) * units + u][0] < min(i, per_kind[1 - k]):
                         continue                                  # token: the other warp of my unit has not finished i tiles yet
                     if (fd & 1) != (lap & 1):                      # consumer parity starts at 0 and flips every lap
                         if content != n:
@@ -122,7 +127,7 @@ def check(layout, units=2, ntiles=24, coupled=False, max_states=4_000_000):
                     nc[k * units + u] = (i + 1, 0)
                     succ.append((prod_n, tuple(nc), tuple(ns_)))
         if not succ:
-            done = prod_n == ntiles and all(cons[k * units + u][0] >= per_kind[k] for k in range(2) for u in range(units))
+            done = prod_n == ntiles and all(cons[k * units + u][0] >= per_kind[k] for k in range(nk) for u in range(units))
             if not done:
                 return "deadlock", len(seen)
         for nx in succ:
@@ -135,7 +140,7 @@ def check(layout, units=2, ntiles=24, coupled=False, max_states=4_000_000):
 
 
 if __name__ == "__main__":
-    for layout in (("one", 5), ("one", 4), ("two", 3, 2), ("two", 2, 2), ("two", 3, 1)):
+    for layout in (("one", 5), ("one", 4), ("two", 3, 2), ("two", 2, 2), ("two", 3, 1), ("all", 5), ("all", 10)):
         for coupled in (True, False):
             res, n = check(layout, units=2, ntiles=24, coupled=coupled)
             print(f"{layout!s:18} {'token-coupled' if coupled else 'free-running '}  {res}  ({n} states)")
