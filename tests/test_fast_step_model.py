@@ -1,0 +1,73 @@
+"""One blind-rotation step of the FAST path, assembled on the CPU from the numpy models of its parts, against the oracle's step
+(bootstrapping.jl:413-438, `orc_cmux_step`) on the same accumulator row, key and rotation:
+
+    field-extraction digits (csrc/kernels_fast_w.cuh)  ->  product-tree transform in the kernel's thread / register order
+    (tools/models/fft32_model.py)  ->  spectrum x key into both sums  ->  x (X^a - 1) from the reference's monomial table
+    ->  inverse in the kernel's order  ->  floor onto the torus (fast::d2torus)  ->  accumulator +=
+
+The model uses numpy complex arithmetic instead of the kernel's fused multiply-adds, so it is not bit-equal to the GPU; what it pins
+on the CPU is everything else a FAST step consists of -- which digit meets which key polynomial, the slot order, the monomial
+convention, the sign of the folded halves -- and that this schedule of Float64 operations stays within the tolerance the GPU test
+states (2^33 on Torus64, tests/test_gpu_fast.py) of the reference's schedule.  CPU only."""
+import importlib.util
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import keyset, make_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL_LOG2 = 33
+
+
+def _model():
+    spec = importlib.util.spec_from_file_location("fft32_model", os.path.join(ROOT, "tools", "models", "fft32_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _digits(x, l, logB, w=64):
+    """FAST decomposition: bit fields of x + cadd (tests/test_transform_models.py checks them against gsw.jl:86-96)."""
+    bit = w - l * logB
+    cadd = (1 << (bit - 1)) + sum(1 << (bit + j * logB + logB - 1) for j in range(l))
+    mask, half = (1 << logB) - 1, 1 << (logB - 1)
+    v = [(int(c) + cadd) % (1 << w) for c in x]
+    return [np.array([((c >> (bit + (l - 1 - j) * logB)) & mask) - half for c in v], dtype=np.float64) for j in range(l)]
+
+
+@pytest.mark.parametrize("name,party,idx,at", [("KMS2party", 0, 0, 1), ("KMS2party", 1, 17, 2047), ("KMS2party", 1, 559, 2048),
+                                               ("KMS2party", 0, 300, 4095), ("KMS2partyblock", 1, 5, 1234)])
+def test_fast_step_model_within_tolerance_of_the_reference_step(name, party, idx, at):
+    from oracle import oracle as O
+    m = _model()
+    ks = keyset(name)
+    p = ks.params
+    orc = make_oracle(ks)
+    N, H, l, logB = p.N, p.N // 2, p.l_gsw, p.logB_gsw
+    rng = np.random.default_rng(1000 * idx + at)
+    acc = rng.integers(0, 2 ** 64, size=(2, N), dtype=np.uint64)             # one RLWE row: b, a
+    want = orc.cmux_step(party, idx, at, acc)
+
+    brk = ks.brk[party][idx].reshape(2, l, 2, H, 2)                           # [basket b | a][digit][component b | a][slot](re, im)
+    key = brk[..., 0] + 1j * brk[..., 1]
+    sums = np.zeros((2, H), dtype=complex)
+    for basket in range(2):                                                   # digits of acc.b meet basket 0, of acc.a basket 1
+        for j, d in enumerate(_digits(acc[basket], l, logB)):
+            spec = m.fwd(d[:H] - 1j * d[H:])                                  # the kernel's folding: c_k = p_k - i p_{k+H}
+            for comp in range(2):
+                sums[comp] += spec * key[basket, j, comp]
+    mono = O.monomials(N)[at - 1]
+    mono = mono[:, 0] + 1j * mono[:, 1]                                       # FFT(X^at - 1), scheme.jl:121-146
+    got = acc.copy()
+    for comp in range(2):
+        y = m.inv(sums[comp] * mono) / H
+        add = [math.floor(v) for v in y.real] + [math.floor(-v) for v in y.imag]
+        got[comp] = np.array([(int(a) + b) % 2 ** 64 for a, b in zip(acc[comp], add)], dtype=np.uint64)
+
+    diff = (got.astype(np.int64) - want.astype(np.int64))                     # wraps mod 2^64 = centred difference
+    worst = int(np.abs(diff).max())
+    assert worst < 2 ** TOL_LOG2, math.log2(max(worst, 1))
+    assert worst > 0 or at == 4096                                            # two Float64 schedules: equal words would mean the model IS the oracle
