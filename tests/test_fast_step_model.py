@@ -22,8 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL_LOG2 = 33
 
 
-def _model():
-    spec = importlib.util.spec_from_file_location("fft32_model", os.path.join(ROOT, "tools", "models", "fft32_model.py"))
+def _model(name="fft32_model"):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", "models", name + ".py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m
@@ -32,7 +32,7 @@ def _model():
 def _digits(x, l, logB, w=64):
     """FAST decomposition: bit fields of x + cadd (tests/test_transform_models.py checks them against gsw.jl:86-96)."""
     bit = w - l * logB
-    cadd = (1 << (bit - 1)) + sum(1 << (bit + j * logB + logB - 1) for j in range(l))
+    cadd = ((1 << (bit - 1)) if bit > 0 else 0) + sum(1 << (bit + j * logB + logB - 1) for j in range(l))
     mask, half = (1 << logB) - 1, 1 << (logB - 1)
     v = [(int(c) + cadd) % (1 << w) for c in x]
     return [np.array([((c >> (bit + (l - 1 - j) * logB)) & mask) - half for c in v], dtype=np.float64) for j in range(l)]
@@ -71,3 +71,35 @@ def test_fast_step_model_within_tolerance_of_the_reference_step(name, party, idx
     worst = int(np.abs(diff).max())
     assert worst < 2 ** TOL_LOG2, math.log2(max(worst, 1))
     assert worst > 0 or at == 4096                                            # two Float64 schedules: equal words would mean the model IS the oracle
+
+
+@pytest.mark.parametrize("idx,at", [(0, 1), (629, 1023), (77, 1024), (400, 2047)])
+def test_fast_step_model_torus32(idx, at):
+    """The same for the Torus32 single-key step (bootstrapping.jl:47-74) with the half-warp transform order of fastw32::k_cggi_w
+    (tools/models/fft16x32_model.py): within 1 unit of Torus32 (the GPU test allows 4)."""
+    from oracle import oracle as O
+    m = _model("fft16x32_model")
+    ks = keyset("CGGIparam")
+    p = ks.params
+    orc = make_oracle(ks)
+    N, H, l, logB = p.N, p.N // 2, p.l_gsw, p.logB_gsw
+    rng = np.random.default_rng(7000 + 10 * idx + at)
+    acc = rng.integers(0, 2 ** 32, size=(2, N), dtype=np.uint32)
+    want = orc.cmux_step(0, idx, at, acc)
+    brk = ks.brk[0][idx].reshape(2, l, 2, H, 2)
+    key = brk[..., 0] + 1j * brk[..., 1]
+    sums = np.zeros((2, H), dtype=complex)
+    for basket in range(2):
+        for j, d in enumerate(_digits(acc[basket], l, logB, w=32)):
+            spec = m.fwd(d[:H] - 1j * d[H:])
+            for comp in range(2):
+                sums[comp] += spec * key[basket, j, comp]
+    mono = O.monomials(N)[at - 1]
+    mono = mono[:, 0] + 1j * mono[:, 1]
+    got = acc.copy()
+    for comp in range(2):
+        y = m.inv(sums[comp] * mono) / H
+        add = [math.floor(v) for v in y.real] + [math.floor(-v) for v in y.imag]
+        got[comp] = np.array([(int(a) + b) % 2 ** 32 for a, b in zip(acc[comp], add)], dtype=np.uint32)
+    diff = (got.astype(np.int64) - want.astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
+    assert int(np.abs(diff).max()) <= 1, int(np.abs(diff).max())
