@@ -103,3 +103,43 @@ def test_fast_step_model_torus32(idx, at):
         got[comp] = np.array([(int(a) + b) % 2 ** 32 for a, b in zip(acc[comp], add)], dtype=np.uint32)
     diff = (got.astype(np.int64) - want.astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
     assert int(np.abs(diff).max()) <= 1, int(np.abs(diff).max())
+
+
+@pytest.mark.parametrize("party,blk,ats", [(0, 0, (1, 2, 3)), (1, 40, (4095, 0, 2048)), (1, 100, (0, 0, 0)), (0, 186, (777, 777, 1))])
+def test_block_step_with_monomials_folded_into_the_keys(party, blk, ats):
+    """KMS_block step (bootstrapping.jl:624-655; LMSS :124-163): the reference forms one external product per key bit of a block and
+    adds mono_bit x product.  fast::k_phase1_tma<3> keeps ONE pair of sums per block by folding the monomials into the keys,
+    Sum_bit mono_bit (Sum_dg D_dg K_bit,dg) = Sum_dg D_dg (Sum_bit mono_bit K_bit,dg), and skips bits with a~ = 0 like the reference.
+    The folded form, assembled from the numpy models, must land within 2^33 of the oracle's block step (the GPU measures 2^31.9)."""
+    from oracle import oracle as O
+    m = _model()
+    ks = keyset("KMS2partyblock")
+    p = ks.params
+    orc = make_oracle(ks)
+    N, H, l, logB, ell = p.N, p.N // 2, p.l_gsw, p.logB_gsw, p.ell
+    rng = np.random.default_rng(blk * 7 + sum(ats))
+    acc = rng.integers(0, 2 ** 64, size=(2, N), dtype=np.uint64)
+    want = orc.block_step(party, blk, np.array(ats, dtype=np.uint32), acc)
+    table = O.monomials(N)
+    folded = np.zeros((2, l, 2, H), dtype=complex)                            # [basket][digit][component][slot]
+    for bit, at in enumerate(ats):
+        if at == 0:
+            continue                                                          # :637 `if tildea[idx] > 0`
+        brk = ks.brk[party][blk * ell + bit].reshape(2, l, 2, H, 2)
+        mono = table[at - 1][:, 0] + 1j * table[at - 1][:, 1]
+        folded += (brk[..., 0] + 1j * brk[..., 1]) * mono
+    sums = np.zeros((2, H), dtype=complex)
+    for basket in range(2):
+        for j, d in enumerate(_digits(acc[basket], l, logB)):
+            spec = m.fwd(d[:H] - 1j * d[H:])
+            for comp in range(2):
+                sums[comp] += spec * folded[basket, j, comp]
+    got = acc.copy()
+    for comp in range(2):
+        y = m.inv(sums[comp]) / H
+        add = [math.floor(v) for v in y.real] + [math.floor(-v) for v in y.imag]
+        got[comp] = np.array([(int(a) + b) % 2 ** 64 for a, b in zip(acc[comp], add)], dtype=np.uint64)
+    worst = int(np.abs(got.astype(np.int64) - want.astype(np.int64)).max())
+    assert worst < 2 ** TOL_LOG2, math.log2(max(worst, 1))
+    if not any(ats):
+        assert worst <= 1                                                     # nothing to add: floor(0) against native(0 +- rounding)
