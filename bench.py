@@ -269,6 +269,8 @@ def main():
 # BASELINE.json configs[0] (CGGI), configs[2] (KMS 8-party block, 16384 gates over 8 GPUs = 2048 per GPU), configs[3] (CCS 16-party),
 # configs[4] (KMS 32-party); "kms8" is the k = 8 point of BASELINE.json's metric ("k=2/8/32") without block keys
 ALSO = ("cggi", "kms8block", "kms8", "ccs16", "kms32")
+if os.environ.get("MKTFHE_BENCH_ALSO"):          # a shorter list for a quick run, e.g. MKTFHE_BENCH_ALSO=cggi
+    ALSO = tuple(w for w in os.environ["MKTFHE_BENCH_ALSO"].split(",") if w in WORKLOADS)
 # Where the evaluation keys come from.  "host": libmktfhe_host.so on rank 0, pinned upload, NCCL broadcast to the other ranks (the
 # reference's flow: keys are built on the host).  "device": generated on every GPU from the seed (byte-identical, no PCIe / NVLink).
 # The headline keeps the host path; the 10.6 GB key set of KMS32party takes 15 s + 3 s that way and 2 s on the device.
